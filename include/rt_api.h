@@ -1,0 +1,198 @@
+/*
+ * rt_api.h -- the drop-in boundary of the B200 render path (C ABI, no torch / C++ types).
+ *
+ * The reference (Sh-Anand/Raytracer-in-CPP) has no FFI: its hot path is a set of C++ member
+ * functions of Flyscene / BoxTree / BoundingBox / arealight.  Each entry point
+ * below names the reference interface it replaces (file:line relative to /root/reference); the
+ * C++ facade in raytracer-in-cpp_b200/host/flyscene.hpp keeps the reference's class and method
+ * names and forwards to these functions, and INTEGRATION.md shows the binding a maintainer of the
+ * reference would add inside src/flyscene.cpp.
+ *
+ * Conventions (all taken from the reference):
+ *   - ray directions are NOT normalised; t is in units of |d|
+ *   - pixel (i, j): i = column, j = row, row 0 is the top of the image, integer corner (no +0.5)
+ *   - colours are float RGB in [0,1]; 8-bit = min(255, (int)(255*c))   (tucano/utils/ppmIO.hpp:145)
+ *   - BACKGROUND = (1,1,1), SHADOW = (0,0,0)                            (src/flyscene.cpp:12-13)
+ *   - "no hit" face id = -1, t = FLT_MAX
+ *
+ * Every function returns 0 on success or a negative RtStatus; rt_last_error() gives the message
+ * (thread-local).  There is NO CPU fallback: without a CUDA device every compute entry point fails
+ * with RT_ERR_NO_DEVICE.  All calls are blocking unless a stream is passed.
+ */
+#ifndef RT_API_H
+#define RT_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API_VERSION 1
+#define RT_MAX_LIGHTS 25   /* bool visibleLights[25], src/flyscene.cpp:699,835 */
+#define RT_MAX_SAMPLES 25
+
+typedef enum {
+  RT_OK = 0,
+  RT_ERR_INVALID = -1,    /* bad argument */
+  RT_ERR_NO_DEVICE = -2,  /* no CUDA device / CUDA runtime failure at init */
+  RT_ERR_CUDA = -3,       /* CUDA call failed; see rt_last_error() */
+  RT_ERR_IO = -4,         /* file could not be read / written */
+  RT_ERR_LIMIT = -5       /* more than RT_MAX_LIGHTS lights or RT_MAX_SAMPLES samples */
+} RtStatus;
+
+/* Tucano::Material::Mtl as read by the hot path (tucano/materials/mtl.hpp:108-114) */
+typedef struct {
+  float kd[3];
+  float ks[3];
+  float ns;      /* shininess */
+  float ni;      /* optical density */
+  int32_t illum; /* illumination model, drives the material switch src/flyscene.cpp:712-760 */
+} RtMaterial;
+
+/* The baked scene: exactly the values the reference's inner loops read per face
+ * (src/flyscene.cpp:788-792, 867-872, 712-713).  Caller keeps ownership; rt_scene_create copies. */
+typedef struct {
+  int32_t n_faces;
+  const float *verts;           /* [T][3][3] world space: (mesh.getShapeModelMatrix()*v).head<3>() */
+  const float *face_normals;    /* [T][3]    Tucano::Face::normal */
+  const float *vertex_normals;  /* [T][3][3] mesh.getNormal(face.vertex_ids[k]) */
+  const int32_t *material_id;   /* [T]       Tucano::Face::material_id */
+  int32_t n_materials;
+  const RtMaterial *materials;
+  float model_matrix[12];       /* 3x4 row-major mesh.getModelMatrix(), applied to the shading normal (:829) */
+  int32_t n_spheres;            /* analytic spheres: NOT in the reference (BASELINE config 4), may be 0 */
+  const float *spheres;         /* [S][4] centre, radius */
+  const int32_t *sphere_material; /* [S] */
+} RtSceneDesc;
+
+/* Tucano::Flycamera state read by raytraceScene (src/flyscene.cpp:551,575; tucano/camera.hpp:115-173) */
+typedef struct {
+  float eye[3];        /* flycamera.getCenter() */
+  float view_inv[12];  /* flycamera.getViewMatrix().inverse(), 3x4 row-major */
+  float viewport[4];   /* (0, 0, w, h) */
+  float fovy;          /* degrees (60) */
+  float aspect;        /* w / (float)h */
+} RtCamera;
+
+/* Flyscene::lights + lightrep colour (src/flyscene.cpp:68,72) */
+typedef struct {
+  int32_t n;           /* <= RT_MAX_LIGHTS */
+  const float *pos;    /* [n][3] */
+  float color[3];      /* (1,1,0) in the reference */
+} RtLights;
+
+typedef struct {
+  int32_t width, height;
+  int32_t area_light;        /* stdin flag, src/flyscene.cpp:31-32 */
+  int32_t point_light;       /* stdin flag, src/flyscene.cpp:33-34 (wins over area_light, :964) */
+  int32_t max_depth;         /* rays at level >= max_depth shade as plain Phong; < 0 = reference
+                                behaviour (unbounded; guarded at 64 levels) */
+  int32_t usteps, vsteps;    /* area-light grid, reference 5 x 5 (src/flyscene.cpp:971) */
+  float area_len_x, area_len_y; /* 0.3, 0.15 */
+  /* multi-GPU row-band sharding: this call renders bands b with b % band_world == band_rank,
+   * band = band_rows full-width rows; output buffers then hold only the local rows, packed in
+   * ascending row order.  band_world <= 1 renders the whole image. */
+  int32_t band_rows, band_rank, band_world;
+} RtParams;
+
+typedef struct {
+  int64_t rays_primary;     /* one per rendered pixel */
+  int64_t rays_shadow;      /* any-hit queries traced (gate + sample rays; merged in point mode) */
+  int64_t rays_secondary;   /* reflection / refraction / pass-through rays */
+  int64_t pixels;           /* pixels rendered by this call */
+  int32_t levels;           /* bounce levels executed */
+  float ms_total;           /* device time of the whole call (CUDA events) */
+  float ms_trace;           /* nearest-hit kernels (K1) */
+  float ms_shadow;          /* any-hit kernels (K2) */
+  float ms_shade;           /* shade / compaction / fold / framebuffer kernels (K3) */
+  int32_t kernel_launches;  /* kernels launched by this call */
+  /* traversal work counters, filled only when rt_set_option("stats", 1) */
+  int64_t box_tests, tri_tests, shade_samples;
+} RtStats;
+
+typedef struct RtScene RtScene;   /* device-resident BVH + triangle soup + shading tables */
+typedef struct RtMesh RtMesh;     /* host-side loaded + baked OBJ/MTL */
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+int rt_api_version(void);
+/* Select the CUDA device for this process (one process per GPU).  Replaces nothing in the
+ * reference (CPU only); ThreadPool construction src/flyscene.cpp:609 is the closest analogue. */
+int rt_init(int device);
+void rt_shutdown(void);
+const char *rt_last_error(void);
+int rt_device_name(char *buf, size_t n);
+/* runtime knobs: "stats" (0/1 traversal counters), "leaf_size", "persistent_ctas_per_sm" */
+int rt_set_option(const char *key, int value);
+void rt_default_params(RtParams *p);
+
+/* ---- scene bake (host) --------------------------------------------------------------------- */
+/* Tucano::MeshImporter::loadObjFile + loadMTL + Mesh::normalizeModelMatrix
+ * (tucano/utils/objimporter.hpp:83-284, mtlIO.hpp:45-125, model.hpp:169-173; src/flyscene.cpp:50-56) */
+int rt_mesh_load_obj(const char *obj_path, RtMesh **out);
+/* fills desc with pointers into the mesh (valid until rt_mesh_destroy) */
+int rt_mesh_desc(const RtMesh *mesh, RtSceneDesc *desc);
+/* normalisation data: centroid[3], radius, scale  (tucano/mesh.hpp:621-642) */
+int rt_mesh_info(const RtMesh *mesh, float centroid[3], float *radius, float *scale, int32_t *n_vertices);
+void rt_mesh_destroy(RtMesh *mesh);
+
+/* ---- acceleration structure ---------------------------------------------------------------- */
+/* BoxTree::BoxTree(Mesh&, capacity) + BoundingBox::BoundingBox(Mesh&)
+ * (src/boxTree.cpp:11-31,88-147; src/boundingBox.cpp:14-43; called at src/flyscene.cpp:93).
+ * Builds the flattened BVH on the host and uploads everything once. */
+int rt_scene_create(const RtSceneDesc *desc, RtScene **out);
+void rt_scene_destroy(RtScene *scene);
+/* BoxTree::box (root AABB, reference semantics incl. the FLT_MIN max initialiser) */
+int rt_scene_root_box(const RtScene *scene, float mn[3], float mx[3]);
+/* node / leaf / triangle counts, bytes resident on the device, build milliseconds */
+int rt_scene_info(const RtScene *scene, int64_t *n_nodes, int64_t *n_leaves, int64_t *n_tris,
+                  int64_t *device_bytes, float *build_ms);
+/* debug / test access to the flattened BVH (host copies): nodes [n_nodes][16] floats as uploaded,
+ * tri_face [n_tris] original face id of each soup slot */
+int rt_scene_debug_bvh(const RtScene *scene, float *nodes, int64_t nodes_cap, int32_t *tri_face, int64_t tri_cap);
+
+/* ---- the frame ----------------------------------------------------------------------------- */
+/* Flyscene::raytraceScene (src/flyscene.cpp:519-648) minus the PPM write: host output buffers.
+ *   rgba_out : [rows][W][4] uint8 (A = 255), required
+ *   face_out : [rows][W] int32 primary-hit face id (-1 = none), optional
+ *   t_out    : [rows][W] float primary-hit t, optional
+ *   rgb_f32_out : [rows][W][3] float colour before quantisation, optional
+ * rows = H, or the local row count under band sharding (rt_local_rows). */
+int rt_render(RtScene *scene, const RtCamera *cam, const RtLights *lights, const RtParams *params,
+              uint8_t *rgba_out, int32_t *face_out, float *t_out, float *rgb_f32_out, RtStats *stats);
+/* Same, outputs are DEVICE pointers (may be NULL except d_rgba); stream = cudaStream_t or NULL.
+ * Asynchronous with respect to the host when stats == NULL. */
+int rt_render_device(RtScene *scene, const RtCamera *cam, const RtLights *lights, const RtParams *params,
+                     void *d_rgba, int32_t *d_face, float *d_t, float *d_rgb_f32, void *stream, RtStats *stats);
+int rt_local_rows(const RtParams *params);
+/* global row index of each local row (ascending); rows_out has rt_local_rows entries */
+int rt_local_row_map(const RtParams *params, int32_t *rows_out);
+
+/* ---- per-function entry points (batched) --------------------------------------------------- */
+/* Flyscene::traceRay (src/flyscene.cpp:651-771) for n arbitrary rays: rgb_out [n][3] float,
+ * face_out / t_out optional.  level-0 semantics (lights = the scene lights). Host pointers. */
+int rt_trace_rays(RtScene *scene, int64_t n, const float *origins, const float *dirs, const RtLights *lights,
+                  const RtParams *params, float *rgb_out, int32_t *face_out, float *t_out);
+/* Flyscene::lightStrikes (src/flyscene.cpp:912-954): n hit points x lights->n lights,
+ * visible_out [n][lights->n] uint8 */
+int rt_light_strikes(RtScene *scene, int64_t n, const float *hit_points, const RtLights *lights,
+                     uint8_t *visible_out);
+/* BoundingBox::boxIntersect (src/boundingBox.cpp:48-83) against the scene root box for n segments
+ * origin -> dest; hit_out [n] uint8 */
+int rt_box_intersect(RtScene *scene, int64_t n, const float *origins, const float *dests, uint8_t *hit_out);
+/* Camera::screenToWorld (tucano/camera.hpp:155-173) for n pixel coordinates; out [n][3] */
+int rt_screen_to_world(const RtCamera *cam, int64_t n, const float *pixels_xy, float *out);
+/* Flyscene::createSpherePoint / arealight::getPointLights (src/flyscene.cpp:962-972,
+ * arealight.hpp:15-25): host-side, returns the sample count (<= RT_MAX_SAMPLES) or < 0 */
+int rt_light_samples(const RtParams *params, const float light[3], float *out /*[25][3]*/);
+
+/* ---- output -------------------------------------------------------------------------------- */
+/* Tucano::ImageImporter::writePPMImage (tucano/utils/ppmIO.hpp:130-151): ASCII P3, "r g b " per
+ * pixel, one text line per image row.  binary != 0 writes P6 instead. */
+int rt_write_ppm(const char *path, const uint8_t *rgba, int32_t width, int32_t height, int32_t binary);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_API_H */

@@ -1,0 +1,384 @@
+"""ctypes binding of the C ABI (include/rt_api.h) exported by librt_b200.so.
+
+This is plumbing for tests and bench.py: every compute call goes through the C ABI into the CUDA
+kernels.  There is no CPU path here -- if the shared library is missing, or no CUDA device is
+present, the calls raise RtError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librt_b200.so")
+
+RT_MAX_LIGHTS = 25
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rt error {code}: {msg}")
+        self.code = code
+
+
+class RtMaterial(C.Structure):
+    _fields_ = [("kd", C.c_float * 3), ("ks", C.c_float * 3), ("ns", C.c_float), ("ni", C.c_float),
+                ("illum", C.c_int32)]
+
+
+class RtSceneDesc(C.Structure):
+    _fields_ = [("n_faces", C.c_int32), ("verts", C.c_void_p), ("face_normals", C.c_void_p),
+                ("vertex_normals", C.c_void_p), ("material_id", C.c_void_p), ("n_materials", C.c_int32),
+                ("materials", C.c_void_p), ("model_matrix", C.c_float * 12), ("n_spheres", C.c_int32),
+                ("spheres", C.c_void_p), ("sphere_material", C.c_void_p)]
+
+
+class RtCamera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("view_inv", C.c_float * 12), ("viewport", C.c_float * 4),
+                ("fovy", C.c_float), ("aspect", C.c_float)]
+
+
+class RtLights(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos", C.c_void_p), ("color", C.c_float * 3)]
+
+
+class RtParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("area_light", C.c_int32),
+                ("point_light", C.c_int32), ("max_depth", C.c_int32), ("usteps", C.c_int32),
+                ("vsteps", C.c_int32), ("area_len_x", C.c_float), ("area_len_y", C.c_float),
+                ("band_rows", C.c_int32), ("band_rank", C.c_int32), ("band_world", C.c_int32)]
+
+
+class RtStats(C.Structure):
+    _fields_ = [("rays_primary", C.c_int64), ("rays_shadow", C.c_int64), ("rays_secondary", C.c_int64),
+                ("pixels", C.c_int64), ("levels", C.c_int32), ("ms_total", C.c_float), ("ms_trace", C.c_float),
+                ("ms_shadow", C.c_float), ("ms_shade", C.c_float), ("kernel_launches", C.c_int32),
+                ("box_tests", C.c_int64), ("tri_tests", C.c_int64), ("shade_samples", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/rt_api.h declares (tests check that the library exports all of them)
+API_SYMBOLS = [
+    "rt_api_version", "rt_init", "rt_shutdown", "rt_last_error", "rt_device_name", "rt_set_option",
+    "rt_default_params", "rt_mesh_load_obj", "rt_mesh_desc", "rt_mesh_info", "rt_mesh_destroy",
+    "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_scene_debug_bvh",
+    "rt_render", "rt_render_device", "rt_local_rows", "rt_local_row_map", "rt_trace_rays",
+    "rt_light_strikes", "rt_box_intersect", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm",
+]
+
+_lib = None
+
+
+def lib():
+    """Load librt_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RtError(-100, f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    L.rt_api_version.restype = C.c_int
+    L.rt_init.argtypes = [C.c_int]
+    L.rt_last_error.restype = C.c_char_p
+    L.rt_device_name.argtypes = [C.c_char_p, C.c_size_t]
+    L.rt_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.rt_default_params.argtypes = [C.POINTER(RtParams)]
+    L.rt_default_params.restype = None
+    L.rt_mesh_load_obj.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.rt_mesh_desc.argtypes = [vp, C.POINTER(RtSceneDesc)]
+    L.rt_mesh_info.argtypes = [vp, vp, vp, vp, vp]
+    L.rt_mesh_destroy.argtypes = [vp]
+    L.rt_mesh_destroy.restype = None
+    L.rt_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(vp)]
+    L.rt_scene_destroy.argtypes = [vp]
+    L.rt_scene_destroy.restype = None
+    L.rt_scene_root_box.argtypes = [vp, vp, vp]
+    L.rt_scene_info.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rt_scene_debug_bvh.argtypes = [vp, vp, i64, vp, i64]
+    L.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp, vp, vp]
+    L.rt_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp,
+                                   vp, vp, vp]
+    L.rt_local_rows.argtypes = [C.POINTER(RtParams)]
+    L.rt_local_row_map.argtypes = [C.POINTER(RtParams), vp]
+    L.rt_trace_rays.argtypes = [vp, i64, f32p, f32p, C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp]
+    L.rt_light_strikes.argtypes = [vp, i64, f32p, C.POINTER(RtLights), vp]
+    L.rt_box_intersect.argtypes = [vp, i64, f32p, f32p, vp]
+    L.rt_screen_to_world.argtypes = [C.POINTER(RtCamera), i64, f32p, vp]
+    L.rt_light_samples.argtypes = [C.POINTER(RtParams), vp, vp]
+    L.rt_write_ppm.argtypes = [C.c_char_p, vp, i32, i32, i32]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise RtError(rc, lib().rt_last_error().decode(errors="replace"))
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def init(device: int = 0):
+    _check(lib().rt_init(device))
+
+
+def device_name() -> str:
+    buf = C.create_string_buffer(256)
+    _check(lib().rt_device_name(buf, 256))
+    return buf.value.decode()
+
+
+def set_option(key: str, value: int):
+    _check(lib().rt_set_option(key.encode(), int(value)))
+
+
+def make_params(width, height, area=0, point=1, max_depth=-1, grid=(5, 5), band_rows=8, band_rank=0,
+                band_world=1) -> RtParams:
+    p = RtParams()
+    lib().rt_default_params(C.byref(p))
+    p.width, p.height = int(width), int(height)
+    p.area_light, p.point_light = int(area), int(point)
+    p.max_depth = int(max_depth)
+    p.usteps, p.vsteps = int(grid[0]), int(grid[1])
+    p.band_rows, p.band_rank, p.band_world = int(band_rows), int(band_rank), int(band_world)
+    return p
+
+
+def make_camera(eye, view_inv, viewport, fovy, aspect) -> RtCamera:
+    cam = RtCamera()
+    for k in range(3):
+        cam.eye[k] = float(eye[k])
+    vi = np.asarray(view_inv, np.float32).reshape(-1)
+    for k in range(12):
+        cam.view_inv[k] = float(vi[k])
+    for k in range(4):
+        cam.viewport[k] = float(viewport[k])
+    cam.fovy = float(fovy)
+    cam.aspect = float(aspect)
+    return cam
+
+
+def default_camera(width, height) -> RtCamera:
+    """Flycamera reset state (tucano/utils/flycamera.hpp:76-86): eye (0,0,2) looking down -z,
+    fovy 60, aspect w/h (src/flyscene.cpp:46-47)."""
+    vi = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2]], np.float32)
+    return make_camera((0, 0, 2), vi, (0, 0, width, height), 60.0, np.float32(width) / np.float32(height))
+
+
+class Lights:
+    def __init__(self, pos, color=(1.0, 1.0, 0.0)):
+        self.pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        self.c = RtLights()
+        self.c.n = self.pos.shape[0]
+        self.c.pos = _ptr(self.pos)
+        for k in range(3):
+            self.c.color[k] = float(color[k])
+
+
+@dataclass
+class Frame:
+    rgba: np.ndarray          # [rows, W, 4] uint8
+    face: np.ndarray | None   # [rows, W] int32
+    t: np.ndarray | None      # [rows, W] float32
+    rgb: np.ndarray | None    # [rows, W, 3] float32
+    stats: dict | None
+
+
+class Mesh:
+    """Host-side OBJ/MTL load + bake (rt_mesh_load_obj)."""
+
+    def __init__(self, obj_path: str):
+        self.h = C.c_void_p()
+        _check(lib().rt_mesh_load_obj(obj_path.encode(), C.byref(self.h)))
+        self.desc = RtSceneDesc()
+        _check(lib().rt_mesh_desc(self.h, C.byref(self.desc)))
+
+    def arrays(self):
+        T = self.desc.n_faces
+        M = self.desc.n_materials
+
+        def arr(ptr, n, dt):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(dt)), shape=(n,)).copy() if n else np.zeros(0, dt)
+
+        verts = arr(self.desc.verts, T * 9, C.c_float).reshape(T, 3, 3)
+        fn = arr(self.desc.face_normals, T * 3, C.c_float).reshape(T, 3)
+        vn = arr(self.desc.vertex_normals, T * 9, C.c_float).reshape(T, 3, 3)
+        mid = arr(self.desc.material_id, T, C.c_int32)
+        mats = np.zeros((M, 9), np.float32)
+        mp = C.cast(self.desc.materials, C.POINTER(RtMaterial))
+        for m in range(M):
+            mats[m] = list(mp[m].kd) + list(mp[m].ks) + [mp[m].ns, mp[m].ni, mp[m].illum]
+        return verts, fn, vn, mid, mats
+
+    def info(self):
+        c = np.zeros(3, np.float32)
+        r = C.c_float()
+        s = C.c_float()
+        nv = C.c_int32()
+        _check(lib().rt_mesh_info(self.h, _ptr(c), C.byref(r), C.byref(s), C.byref(nv)))
+        return c, r.value, s.value, nv.value
+
+    def close(self):
+        if self.h:
+            lib().rt_mesh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scene:
+    """Device-resident scene (rt_scene_create): flattened BVH + triangle soup + shading tables."""
+
+    def __init__(self, verts, fnormals, vnormals, mat_id, mats, model_matrix=None, spheres=None, sphere_mat=None):
+        self._keep = []
+
+        def keep(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a)
+            return a
+
+        d = RtSceneDesc()
+        verts = keep(verts, np.float32)
+        d.n_faces = int(verts.reshape(-1, 9).shape[0]) if verts.size else 0
+        d.verts = _ptr(verts)
+        d.face_normals = _ptr(keep(fnormals, np.float32))
+        d.vertex_normals = _ptr(keep(vnormals, np.float32))
+        d.material_id = _ptr(keep(mat_id, np.int32))
+        mats = np.asarray(mats, np.float32).reshape(-1, 9)
+        M = mats.shape[0]
+        cm = (RtMaterial * M)()
+        for m in range(M):
+            for k in range(3):
+                cm[m].kd[k] = float(mats[m, k])
+                cm[m].ks[k] = float(mats[m, 3 + k])
+            cm[m].ns, cm[m].ni, cm[m].illum = float(mats[m, 6]), float(mats[m, 7]), int(mats[m, 8])
+        self._keep.append(cm)
+        d.n_materials = M
+        d.materials = C.cast(cm, C.c_void_p)
+        mm = np.eye(4, dtype=np.float32)[:3] if model_matrix is None else np.asarray(model_matrix, np.float32)
+        for k, v in enumerate(mm.reshape(-1)[:12]):
+            d.model_matrix[k] = float(v)
+        if spheres is not None and len(spheres):
+            sp = keep(spheres, np.float32)
+            d.n_spheres = int(sp.shape[0])
+            d.spheres = _ptr(sp)
+            d.sphere_material = _ptr(keep(sphere_mat, np.int32))
+        self.n_faces = d.n_faces
+        self.h = C.c_void_p()
+        _check(lib().rt_scene_create(C.byref(d), C.byref(self.h)))
+
+    @classmethod
+    def from_mesh(cls, mesh: Mesh, spheres=None, sphere_mat=None):
+        verts, fn, vn, mid, mats = mesh.arrays()
+        return cls(verts, fn, vn, mid, mats, None, spheres, sphere_mat)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rt_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def root_box(self):
+        mn, mx = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        _check(lib().rt_scene_root_box(self.h, _ptr(mn), _ptr(mx)))
+        return mn, mx
+
+    def info(self):
+        v = [C.c_int64() for _ in range(4)]
+        ms = C.c_float()
+        _check(lib().rt_scene_info(self.h, *[C.byref(x) for x in v], C.byref(ms)))
+        return dict(nodes=v[0].value, leaves=v[1].value, prims=v[2].value, device_bytes=v[3].value, build_ms=ms.value)
+
+    def debug_bvh(self):
+        inf = self.info()
+        nodes = np.zeros((inf["nodes"], 16), np.float32)
+        tri = np.zeros(inf["prims"], np.int32)
+        _check(lib().rt_scene_debug_bvh(self.h, _ptr(nodes), nodes.shape[0], _ptr(tri), tri.shape[0]))
+        return nodes, tri
+
+    def render(self, cam: RtCamera, lights: Lights, params: RtParams, want_face=True, want_t=True, want_rgb=True,
+               want_stats=True, out_rgba=None) -> Frame:
+        rows = lib().rt_local_rows(C.byref(params))
+        W = params.width
+        rgba = out_rgba if out_rgba is not None else np.zeros((rows, W, 4), np.uint8)
+        face = np.zeros((rows, W), np.int32) if want_face else None
+        t = np.zeros((rows, W), np.float32) if want_t else None
+        rgb = np.zeros((rows, W, 3), np.float32) if want_rgb else None
+        st = RtStats() if want_stats else None
+        _check(lib().rt_render(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), _ptr(rgba), _ptr(face),
+                               _ptr(t), _ptr(rgb), C.byref(st) if st is not None else None))
+        return Frame(rgba, face, t, rgb, st.as_dict() if st is not None else None)
+
+    def render_device(self, cam, lights, params, d_rgba: int, d_face: int = 0, d_t: int = 0, d_rgb: int = 0,
+                      stream: int = 0, stats: RtStats | None = None):
+        """Outputs are raw device pointers (e.g. torch.Tensor.data_ptr())."""
+        _check(lib().rt_render_device(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), d_rgba or None,
+                                      d_face or None, d_t or None, d_rgb or None, stream or None,
+                                      C.byref(stats) if stats is not None else None))
+
+    def trace_rays(self, origins, dirs, lights: Lights, params: RtParams):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        rgb = np.zeros((n, 3), np.float32)
+        face = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        _check(lib().rt_trace_rays(self.h, n, _ptr(o), _ptr(d), C.byref(lights.c), C.byref(params), _ptr(rgb),
+                                   _ptr(face), _ptr(t)))
+        return rgb, face, t
+
+    def light_strikes(self, hits, lights: Lights):
+        h = np.ascontiguousarray(hits, np.float32).reshape(-1, 3)
+        out = np.zeros((h.shape[0], lights.c.n), np.uint8)
+        _check(lib().rt_light_strikes(self.h, h.shape[0], _ptr(h), C.byref(lights.c), _ptr(out)))
+        return out
+
+    def box_intersect(self, origins, dests):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dests, np.float32).reshape(-1, 3)
+        out = np.zeros(o.shape[0], np.uint8)
+        _check(lib().rt_box_intersect(self.h, o.shape[0], _ptr(o), _ptr(d), _ptr(out)))
+        return out
+
+
+def screen_to_world(cam: RtCamera, pixels_xy):
+    p = np.ascontiguousarray(pixels_xy, np.float32).reshape(-1, 2)
+    out = np.zeros((p.shape[0], 3), np.float32)
+    _check(lib().rt_screen_to_world(C.byref(cam), p.shape[0], _ptr(p), _ptr(out)))
+    return out
+
+
+def light_samples(params: RtParams, light):
+    l = np.ascontiguousarray(light, np.float32)
+    out = np.zeros((25, 3), np.float32)
+    n = _check(lib().rt_light_samples(C.byref(params), _ptr(l), _ptr(out)))
+    return out[:n].copy()
+
+
+def local_row_map(params: RtParams):
+    rows = lib().rt_local_rows(C.byref(params))
+    out = np.zeros(rows, np.int32)
+    _check(lib().rt_local_row_map(C.byref(params), _ptr(out)))
+    return out
+
+
+def write_ppm(path: str, rgba: np.ndarray, binary=False):
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    _check(lib().rt_write_ppm(path.encode(), _ptr(rgba), rgba.shape[1], rgba.shape[0], int(binary)))

@@ -1,0 +1,844 @@
+// rt_api.cu -- implementation of the C ABI in include/rt_api.h: scene bake upload, the per-frame
+// wavefront driver (K1 nearest hit -> K2 shadow -> K3 shade/compact -> ... -> K3b fold) and the
+// batched per-function entry points.  No CPU fallback: every compute entry point needs a CUDA
+// device and fails with RT_ERR_NO_DEVICE otherwise.
+#include "../../include/rt_api.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../host/bvh_builder.hpp"
+#include "../host/obj_loader.hpp"
+#include "rt_kernels.cuh"
+
+using namespace rtd;
+
+// ---------------------------------------------------------------------------------------------
+// errors / globals
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+int g_sm_count = 0;
+int g_opt_stats = 0;
+int g_opt_leaf = 4;
+int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
+
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+int ensure_device() {
+  if (g_device >= 0) return RT_OK;
+  return rt_init(0);
+}
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return RT_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    cap = want;
+    return RT_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return (T *)p; }
+};
+
+struct LevelStore {
+  DevBuf ray_o, ray_d, ray_l, hit_t, hit_face, vis, rec, child, type;
+  int reserve(size_t n, size_t J) {
+    n = std::max<size_t>(n, 1);
+    int rc;
+    if ((rc = ray_o.reserve(n * 16))) return rc;
+    if ((rc = ray_d.reserve(n * 16))) return rc;
+    if ((rc = ray_l.reserve(n * 8))) return rc;
+    if ((rc = hit_t.reserve(n * 4))) return rc;
+    if ((rc = hit_face.reserve(n * 4))) return rc;
+    if ((rc = vis.reserve(n * std::max<size_t>(J, 1)))) return rc;
+    if ((rc = rec.reserve(n * 16))) return rc;
+    if ((rc = child.reserve(n * 4))) return rc;
+    if ((rc = type.reserve(n))) return rc;
+    return RT_OK;
+  }
+  LevelBufs bufs(int n) const {
+    LevelBufs b;
+    b.ray_o = ray_o.as<float4>(); b.ray_d = ray_d.as<float4>(); b.ray_l = ray_l.as<float2>();
+    b.hit_t = hit_t.as<float>(); b.hit_face = hit_face.as<int32_t>(); b.vis = vis.as<uint8_t>();
+    b.rec = rec.as<float4>(); b.child = child.as<int32_t>(); b.type = type.as<uint8_t>();
+    b.n = n;
+    return b;
+  }
+  void release() {
+    ray_o.release(); ray_d.release(); ray_l.release(); hit_t.release(); hit_face.release();
+    vis.release(); rec.release(); child.release(); type.release();
+  }
+};
+
+constexpr int kMaxCounters = 512;
+
+}  // namespace
+
+struct RtMesh {
+  rt::BakedMesh mesh;
+};
+
+struct RtScene {
+  DevScene dev{};
+  DevBuf nodes, prims, shade, mats, spheres, sphere_mat;
+  std::vector<rt::PairNode> h_nodes;
+  std::vector<int32_t> h_prim_face;
+  int64_t n_leaves = 0;
+  float build_ms = 0.f;
+  int bvh_depth = 0;
+  // per-frame workspace
+  std::vector<LevelStore> levels;
+  DevBuf work_counters;   // kMaxCounters x u64
+  DevBuf next_counts;     // kMaxCounters x i32
+  DevBuf counters;        // Counters
+  DevBuf out_rgba, out_face, out_t, out_rgbf, in_a, in_b;
+  int32_t *h_count = nullptr;      // pinned
+  Counters *h_counters = nullptr;  // pinned
+  size_t device_bytes() const { return nodes.cap + prims.cap + shade.cap + mats.cap + spheres.cap + sphere_mat.cap; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_api_version(void) { return RT_API_VERSION; }
+
+extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
+
+extern "C" int rt_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(RT_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= n) return fail(RT_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(RT_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(RT_ERR_NO_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  g_device = device;
+  g_sm_count = prop.multiProcessorCount;
+  return RT_OK;
+}
+
+extern "C" void rt_shutdown(void) { g_device = -1; }
+
+extern "C" int rt_device_name(char *buf, size_t n) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, g_device));
+  snprintf(buf, n, "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  return RT_OK;
+}
+
+extern "C" int rt_set_option(const char *key, int value) {
+  if (!key) return fail(RT_ERR_INVALID, "null option key");
+  if (!strcmp(key, "stats")) g_opt_stats = value ? 1 : 0;
+  else if (!strcmp(key, "leaf_size")) g_opt_leaf = std::max(1, std::min(16, value));
+  else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
+  else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
+  return RT_OK;
+}
+
+extern "C" void rt_default_params(RtParams *p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->width = 1000; p->height = 1000;  // src/main.cpp:8-9
+  p->area_light = 0; p->point_light = 1;
+  p->max_depth = -1;
+  p->usteps = 5; p->vsteps = 5;
+  p->area_len_x = 0.3f; p->area_len_y = 0.15f;
+  p->band_rows = 8; p->band_rank = 0; p->band_world = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side scene bake
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_mesh_load_obj(const char *obj_path, RtMesh **out) {
+  if (!obj_path || !out) return fail(RT_ERR_INVALID, "null argument");
+  try {
+    RtMesh *m = new RtMesh();
+    m->mesh = rt::load_obj(obj_path, true);
+    *out = m;
+    return RT_OK;
+  } catch (const std::exception &ex) {
+    return fail(RT_ERR_IO, "%s", ex.what());
+  }
+}
+
+extern "C" int rt_mesh_desc(const RtMesh *mesh, RtSceneDesc *desc) {
+  if (!mesh || !desc) return fail(RT_ERR_INVALID, "null argument");
+  memset(desc, 0, sizeof(*desc));
+  const rt::BakedMesh &m = mesh->mesh;
+  desc->n_faces = m.n_faces();
+  desc->verts = m.verts.data();
+  desc->face_normals = m.fnormals.data();
+  desc->vertex_normals = m.vnormals.data();
+  desc->material_id = m.mat_id.data();
+  desc->n_materials = (int32_t)m.materials.size();
+  desc->materials = m.materials.data();
+  const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  memcpy(desc->model_matrix, ident, sizeof(ident));
+  return RT_OK;
+}
+
+extern "C" int rt_mesh_info(const RtMesh *mesh, float centroid[3], float *radius, float *scale, int32_t *n_vertices) {
+  if (!mesh) return fail(RT_ERR_INVALID, "null mesh");
+  if (centroid) { centroid[0] = mesh->mesh.centroid.x; centroid[1] = mesh->mesh.centroid.y; centroid[2] = mesh->mesh.centroid.z; }
+  if (radius) *radius = mesh->mesh.radius;
+  if (scale) *scale = mesh->mesh.norm_scale;
+  if (n_vertices) *n_vertices = mesh->mesh.n_vertices();
+  return RT_OK;
+}
+
+extern "C" void rt_mesh_destroy(RtMesh *mesh) { delete mesh; }
+
+// ---------------------------------------------------------------------------------------------
+// scene upload
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+inline float hdot(const float *a, const float *b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+inline float bits(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
+
+int upload(DevBuf &b, const void *src, size_t bytes) {
+  int rc = b.reserve(std::max<size_t>(bytes, 16));
+  if (rc) return rc;
+  if (bytes) CUDA_TRY(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+  return RT_OK;
+}
+
+}  // namespace
+
+extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
+  if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
+  if (desc->n_faces < 0 || desc->n_spheres < 0 || desc->n_materials <= 0)
+    return fail(RT_ERR_INVALID, "bad scene counts (faces %d, spheres %d, materials %d)", desc->n_faces,
+                desc->n_spheres, desc->n_materials);
+  if (desc->n_faces > 0 && (!desc->verts || !desc->face_normals || !desc->vertex_normals || !desc->material_id))
+    return fail(RT_ERR_INVALID, "null face arrays");
+  int rc = ensure_device();
+  if (rc) return rc;
+  const auto t_start = std::chrono::high_resolution_clock::now();
+
+  const int T = desc->n_faces, S = desc->n_spheres, N = T + S;
+  for (int i = 0; i < T; ++i)
+    if (desc->material_id[i] < 0 || desc->material_id[i] >= desc->n_materials)
+      return fail(RT_ERR_INVALID, "face %d has material id %d outside [0,%d)", i, desc->material_id[i], desc->n_materials);
+  for (int i = 0; i < S; ++i)
+    if (desc->sphere_material[i] < 0 || desc->sphere_material[i] >= desc->n_materials)
+      return fail(RT_ERR_INVALID, "sphere %d has a bad material id", i);
+
+  RtScene *sc = new RtScene();
+  // ---- reference root box: BoundingBox(Mesh&), src/boundingBox.cpp:14-43 (max starts at FLT_MIN) ----
+  {
+    float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+    float mx[3] = {std::numeric_limits<float>::min(), std::numeric_limits<float>::min(), std::numeric_limits<float>::min()};
+    for (size_t v = 0; v < (size_t)T * 3; ++v)
+      for (int a = 0; a < 3; ++a) {
+        const float x = desc->verts[3 * v + a];
+        mn[a] = std::min(mn[a], x);
+        mx[a] = std::max(mx[a], x);
+      }
+    memcpy(sc->dev.root_min, mn, 12);
+    memcpy(sc->dev.root_max, mx, 12);
+  }
+  memcpy(sc->dev.model, desc->model_matrix, sizeof(float) * 12);
+
+  // ---- primitive boxes + BVH ----
+  std::vector<rt::Aabb> boxes((size_t)N);
+  std::vector<uint8_t> kind((size_t)N, 0);
+  float gmin[3] = {1e30f, 1e30f, 1e30f}, gmax[3] = {-1e30f, -1e30f, -1e30f};
+  for (int i = 0; i < T; ++i) {
+    const float *v = desc->verts + (size_t)i * 9;
+    for (int a = 0; a < 3; ++a) {
+      boxes[i].mn[a] = std::min(v[a], std::min(v[3 + a], v[6 + a]));
+      boxes[i].mx[a] = std::max(v[a], std::max(v[3 + a], v[6 + a]));
+      gmin[a] = std::min(gmin[a], boxes[i].mn[a]); gmax[a] = std::max(gmax[a], boxes[i].mx[a]);
+    }
+  }
+  for (int i = 0; i < S; ++i) {
+    const float *s = desc->spheres + (size_t)i * 4;
+    for (int a = 0; a < 3; ++a) {
+      boxes[T + i].mn[a] = s[a] - s[3]; boxes[T + i].mx[a] = s[a] + s[3];
+      gmin[a] = std::min(gmin[a], boxes[T + i].mn[a]); gmax[a] = std::max(gmax[a], boxes[T + i].mx[a]);
+    }
+    kind[T + i] = 1;
+  }
+  float diag = 1.f;
+  if (N > 0) {
+    const float dx = gmax[0] - gmin[0], dy = gmax[1] - gmin[1], dz = gmax[2] - gmin[2];
+    diag = std::max(1.f, std::sqrt(dx * dx + dy * dy + dz * dz));
+  }
+  const float pad = 1e-5f * diag;  // see DESIGN.md "conservative culling"
+  const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  rt::BvhBuildResult bvh = rt::build_bvh(boxes, kind, g_opt_leaf, pad, threads);
+  sc->n_leaves = bvh.n_leaves;
+  sc->bvh_depth = bvh.max_depth;
+
+  // ---- primitive soup in leaf order (80 B / primitive) ----
+  std::vector<float> prims((size_t)N * 20, 0.f);
+  sc->h_prim_face.resize((size_t)N);
+  for (int slot = 0; slot < N; ++slot) {
+    const int p = bvh.prim_order[slot];
+    float *q = &prims[(size_t)slot * 20];
+    sc->h_prim_face[slot] = p;
+    if (p < T) {
+      const float *v = desc->verts + (size_t)p * 9;
+      const float *n = desc->face_normals + (size_t)p * 3;
+      const float *a = v, *b = v + 3, *c = v + 6;
+      const float e0[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};  // v0 = vertices[2]-vertices[0], :800
+      const float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};  // v1 = vertices[1]-vertices[0], :801
+      const float d00 = hdot(e0, e0), d01 = hdot(e0, e1), d11 = hdot(e1, e1);
+      const float inv = 1 / (d00 * d11 - d01 * d01);                // :810
+      const int illum = desc->materials[desc->material_id[p]].illum;
+      q[0] = n[0]; q[1] = n[1]; q[2] = n[2]; q[3] = hdot(n, a);    // triangleNormal.dot(vertices[0]), :797
+      q[4] = a[0]; q[5] = a[1]; q[6] = a[2]; q[7] = bits(p);
+      q[8] = e0[0]; q[9] = e0[1]; q[10] = e0[2]; q[11] = d00;
+      q[12] = e1[0]; q[13] = e1[1]; q[14] = e1[2]; q[15] = d11;
+      q[16] = d01; q[17] = inv; q[18] = bits(illum == 9 ? (int32_t)PRIM_ILLUM9 : 0); q[19] = 0.f;
+    } else {
+      const int si = p - T;
+      const float *s = desc->spheres + (size_t)si * 4;
+      const int illum = desc->materials[desc->sphere_material[si]].illum;
+      q[0] = s[0]; q[1] = s[1]; q[2] = s[2]; q[3] = s[3];
+      q[7] = bits(p);
+      q[18] = bits((int32_t)(PRIM_SPHERE | (illum == 9 ? PRIM_ILLUM9 : 0)));
+    }
+  }
+  // ---- shading table in original face order (112 B / face) ----
+  std::vector<float> shade((size_t)std::max(T, 1) * 28, 0.f);
+  for (int i = 0; i < T; ++i) {
+    float *q = &shade[(size_t)i * 28];
+    const float *v = desc->verts + (size_t)i * 9, *vn = desc->vertex_normals + (size_t)i * 9;
+    const float *n = desc->face_normals + (size_t)i * 3;
+    for (int k = 0; k < 3; ++k) {
+      q[4 * k] = v[3 * k]; q[4 * k + 1] = v[3 * k + 1]; q[4 * k + 2] = v[3 * k + 2];
+      q[12 + 4 * k] = vn[3 * k]; q[12 + 4 * k + 1] = vn[3 * k + 1]; q[12 + 4 * k + 2] = vn[3 * k + 2];
+    }
+    q[3] = bits(desc->material_id[i]);
+    q[24] = n[0]; q[25] = n[1]; q[26] = n[2];
+  }
+  std::vector<float> mats((size_t)desc->n_materials * 12, 0.f);
+  for (int m = 0; m < desc->n_materials; ++m) {
+    const RtMaterial &mt = desc->materials[m];
+    float *q = &mats[(size_t)m * 12];
+    q[0] = mt.kd[0]; q[1] = mt.kd[1]; q[2] = mt.kd[2]; q[3] = mt.ns;
+    q[4] = mt.ks[0]; q[5] = mt.ks[1]; q[6] = mt.ks[2]; q[7] = mt.ni;
+    q[8] = bits(mt.illum);
+  }
+
+  sc->h_nodes = bvh.nodes;
+  if ((rc = upload(sc->nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(rt::PairNode))) ||
+      (rc = upload(sc->prims, prims.data(), prims.size() * 4)) ||
+      (rc = upload(sc->shade, shade.data(), shade.size() * 4)) ||
+      (rc = upload(sc->mats, mats.data(), mats.size() * 4)) ||
+      (rc = upload(sc->spheres, desc->spheres, (size_t)S * 16)) ||
+      (rc = upload(sc->sphere_mat, desc->sphere_material, (size_t)S * 4)) ||
+      (rc = sc->work_counters.reserve(kMaxCounters * 8)) || (rc = sc->next_counts.reserve(kMaxCounters * 4)) ||
+      (rc = sc->counters.reserve(sizeof(Counters)))) {
+    rt_scene_destroy(sc);
+    return rc;
+  }
+  if (cudaMallocHost((void **)&sc->h_count, kMaxCounters * sizeof(int32_t)) != cudaSuccess ||
+      cudaMallocHost((void **)&sc->h_counters, sizeof(Counters)) != cudaSuccess) {
+    rt_scene_destroy(sc);
+    return fail(RT_ERR_CUDA, "cudaMallocHost failed");
+  }
+  sc->dev.nodes = sc->nodes.as<float4>();
+  sc->dev.prims = sc->prims.as<float4>();
+  sc->dev.shade = sc->shade.as<float4>();
+  sc->dev.mats = sc->mats.as<float4>();
+  sc->dev.spheres = sc->spheres.as<float4>();
+  sc->dev.sphere_mat = sc->sphere_mat.as<int32_t>();
+  sc->dev.n_faces = T; sc->dev.n_spheres = S; sc->dev.n_prims = N; sc->dev.n_nodes = (int32_t)bvh.nodes.size();
+  sc->build_ms = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_start).count();
+  *out = sc;
+  return RT_OK;
+}
+
+extern "C" void rt_scene_destroy(RtScene *sc) {
+  if (!sc) return;
+  sc->nodes.release(); sc->prims.release(); sc->shade.release(); sc->mats.release();
+  sc->spheres.release(); sc->sphere_mat.release();
+  for (auto &l : sc->levels) l.release();
+  sc->work_counters.release(); sc->next_counts.release(); sc->counters.release();
+  sc->out_rgba.release(); sc->out_face.release(); sc->out_t.release(); sc->out_rgbf.release();
+  sc->in_a.release(); sc->in_b.release();
+  if (sc->h_count) cudaFreeHost(sc->h_count);
+  if (sc->h_counters) cudaFreeHost(sc->h_counters);
+  delete sc;
+}
+
+extern "C" int rt_scene_root_box(const RtScene *sc, float mn[3], float mx[3]) {
+  if (!sc) return fail(RT_ERR_INVALID, "null scene");
+  memcpy(mn, sc->dev.root_min, 12);
+  memcpy(mx, sc->dev.root_max, 12);
+  return RT_OK;
+}
+
+extern "C" int rt_scene_info(const RtScene *sc, int64_t *n_nodes, int64_t *n_leaves, int64_t *n_tris,
+                             int64_t *device_bytes, float *build_ms) {
+  if (!sc) return fail(RT_ERR_INVALID, "null scene");
+  if (n_nodes) *n_nodes = sc->dev.n_nodes;
+  if (n_leaves) *n_leaves = sc->n_leaves;
+  if (n_tris) *n_tris = sc->dev.n_prims;
+  if (device_bytes) *device_bytes = (int64_t)sc->device_bytes();
+  if (build_ms) *build_ms = sc->build_ms;
+  return RT_OK;
+}
+
+extern "C" int rt_scene_debug_bvh(const RtScene *sc, float *nodes, int64_t nodes_cap, int32_t *tri_face, int64_t tri_cap) {
+  if (!sc) return fail(RT_ERR_INVALID, "null scene");
+  if (nodes) {
+    if (nodes_cap < (int64_t)sc->h_nodes.size()) return fail(RT_ERR_INVALID, "nodes buffer too small");
+    memcpy(nodes, sc->h_nodes.data(), sc->h_nodes.size() * sizeof(rt::PairNode));
+  }
+  if (tri_face) {
+    if (tri_cap < (int64_t)sc->h_prim_face.size()) return fail(RT_ERR_INVALID, "tri buffer too small");
+    memcpy(tri_face, sc->h_prim_face.data(), sc->h_prim_face.size() * 4);
+  }
+  return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame driver
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_local_rows(const RtParams *p) {
+  if (!p || p->height <= 0) return 0;
+  if (p->band_world <= 1) return p->height;
+  const int B = std::max(1, p->band_rows);
+  const int bands = (p->height + B - 1) / B;
+  int rows = 0;
+  for (int b = p->band_rank; b < bands; b += p->band_world) rows += std::min(B, p->height - b * B);
+  return rows;
+}
+
+extern "C" int rt_local_row_map(const RtParams *p, int32_t *rows_out) {
+  if (!p || !rows_out) return fail(RT_ERR_INVALID, "null argument");
+  if (p->band_world <= 1) { for (int r = 0; r < p->height; ++r) rows_out[r] = r; return RT_OK; }
+  const int B = std::max(1, p->band_rows);
+  const int bands = (p->height + B - 1) / B;
+  int k = 0;
+  for (int b = p->band_rank; b < bands; b += p->band_world)
+    for (int r = b * B; r < std::min(p->height, (b + 1) * B); ++r) rows_out[k++] = r;
+  return RT_OK;
+}
+
+namespace {
+
+int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, const RtParams *p) {
+  memset(&fp, 0, sizeof(fp));
+  if (!lights || !p) return fail(RT_ERR_INVALID, "null lights/params");
+  if (lights->n < 0 || lights->n > RT_MAX_LIGHTS)
+    return fail(RT_ERR_LIMIT, "%d lights: the reference's visibleLights[25] buffer caps lights at %d", lights->n, RT_MAX_LIGHTS);
+  if (lights->n > 0 && !lights->pos) return fail(RT_ERR_INVALID, "null light positions");
+  if (!p->point_light && !p->area_light)
+    return fail(RT_ERR_INVALID, "spherical random light mode (areaLight=0, pointLight=0) is not reproducible "
+                                "(std::random_device, src/flyscene.cpp:974-993) and is not supported");
+  if (!p->point_light) {
+    if (p->usteps <= 0 || p->vsteps <= 0 || p->usteps * p->vsteps > RT_MAX_SAMPLES)
+      return fail(RT_ERR_LIMIT, "area grid %dx%d exceeds %d samples (visibleLights[25])", p->usteps, p->vsteps, RT_MAX_SAMPLES);
+  }
+  if (cam) {
+    memcpy(fp.eye, cam->eye, 12);
+    memcpy(fp.view_inv, cam->view_inv, 48);
+    memcpy(fp.viewport, cam->viewport, 16);
+    // Camera::getPerspectiveScale / screenToWorld scale, tucano/camera.hpp:166-168,263-266
+    const float pscale = (float)((double)1.0f / std::tan((double)(cam->fovy / 2.0f) * (M_PI / (double)180.0f)));
+    const float scale = (float)(1.0 / (double)pscale);
+    fp.cam_sx = cam->aspect * scale;
+    fp.cam_sy = scale;
+  }
+  fp.width = p->width; fp.height = p->height;
+  fp.band_rows = std::max(1, p->band_rows); fp.band_rank = p->band_rank; fp.band_world = p->band_world;
+  fp.local_rows = rt_local_rows(p);
+  fp.n_lights = lights->n;
+  for (int i = 0; i < lights->n * 3; ++i) fp.lights[i] = lights->pos[i];
+  memcpy(fp.light_color, lights->color, 12);
+  fp.area_light = p->area_light; fp.point_light = p->point_light;
+  fp.usteps = p->usteps; fp.vsteps = p->vsteps;
+  fp.area_len_x = p->area_len_x; fp.area_len_y = p->area_len_y;
+  fp.max_depth = p->max_depth;
+  fp.guard_depth = 64;
+  return RT_OK;
+}
+
+struct EventTimer {
+  struct Span { int cat; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  bool on = false;
+  cudaStream_t st = nullptr;
+  void begin(int cat) {
+    if (!on) return;
+    Span s; s.cat = cat;
+    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+    cudaEventRecord(s.a, st);
+    spans.push_back(s);
+  }
+  void end() { if (on) cudaEventRecord(spans.back().b, st); }
+  void collect(float out[4]) {
+    for (auto &s : spans) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, s.a, s.b);
+      out[s.cat] += ms;
+      cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    spans.clear();
+  }
+};
+
+template <class K>
+int persistent_grid(K kernel, int block) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+  if (per_sm < 1) per_sm = 1;
+  if (g_opt_ctas_per_sm > 0) per_sm = std::min(per_sm, g_opt_ctas_per_sm);
+  return per_sm * std::max(1, g_sm_count);
+}
+
+// Runs the wavefront pipeline.  Level 0 is either generated from the camera (n0 = local pixels)
+// or taken from rays already stored in level-0 queue buffers (explicit = true).
+int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0, uchar4 *d_rgba, int32_t *d_face,
+                 float *d_t, float *d_rgbf, cudaStream_t st, RtStats *stats) {
+  const bool want_stats = stats != nullptr;
+  const bool trav_stats = g_opt_stats != 0;
+  EventTimer timer; timer.on = want_stats; timer.st = st;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  if (want_stats) { cudaEventCreate(&ev_a); cudaEventCreate(&ev_b); cudaEventRecord(ev_a, st); }
+
+  const int Lmax = std::max(1, fp.n_lights);
+  const int S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
+  const int J = Lmax + Lmax * S;
+  const int depth_cap = fp.max_depth >= 0 ? fp.max_depth : fp.guard_depth;
+
+  CUDA_TRY(cudaMemsetAsync(sc->work_counters.p, 0, kMaxCounters * 8, st));
+  CUDA_TRY(cudaMemsetAsync(sc->next_counts.p, 0, kMaxCounters * 4, st));
+  CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, sizeof(Counters), st));
+  unsigned long long *wc = sc->work_counters.as<unsigned long long>();
+  int *nc = sc->next_counts.as<int>();
+  Counters *ctr = sc->counters.as<Counters>();
+  int wc_used = 0, launches = 0;
+
+  if ((int)sc->levels.size() < 1) sc->levels.resize(1);
+  int rc = sc->levels[0].reserve((size_t)n0, (size_t)J);
+  if (rc) return rc;
+
+  std::vector<int> level_n;
+  level_n.push_back(n0);
+  int64_t secondary = 0;
+
+  const int grid_k1p = trav_stats ? persistent_grid(k_trace_nearest<true, true>, 128) : persistent_grid(k_trace_nearest<true, false>, 128);
+  const int grid_k1s = trav_stats ? persistent_grid(k_trace_nearest<false, true>, 128) : persistent_grid(k_trace_nearest<false, false>, 128);
+  const int grid_k2 = trav_stats ? persistent_grid(k_shadow<true>, 128) : persistent_grid(k_shadow<false>, 128);
+
+  for (int level = 0;; ++level) {
+    const int n = level_n[level];
+    LevelBufs lv = sc->levels[level].bufs(n);
+    if (wc_used + 2 >= kMaxCounters) return fail(RT_ERR_LIMIT, "too many bounce levels");
+    // ---- K1 ----
+    timer.begin(0);
+    if (level == 0 && !explicit_rays) {
+      const int tiles = ((fp.width + 7) / 8) * ((fp.local_rows + 3) / 4);
+      const int items = tiles * 32;
+      if (trav_stats) k_trace_nearest<true, true><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, items, wc + wc_used, d_face, d_t, ctr);
+      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, items, wc + wc_used, d_face, d_t, ctr);
+    } else {
+      if (trav_stats) k_trace_nearest<false, true><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, n, wc + wc_used, nullptr, nullptr, ctr);
+      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, n, wc + wc_used, nullptr, nullptr, ctr);
+    }
+    timer.end();
+    ++wc_used; ++launches;
+    // ---- K2 ----
+    timer.begin(1);
+    const unsigned long long jobs = (unsigned long long)n * (unsigned)J;
+    if (trav_stats) k_shadow<true><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, J, Lmax, S, jobs, wc + wc_used, ctr);
+    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, J, Lmax, S, jobs, wc + wc_used, ctr);
+    timer.end();
+    ++wc_used; ++launches;
+    // ---- K3 ----
+    const bool may_spawn = level < depth_cap;
+    if ((int)sc->levels.size() < level + 2) sc->levels.resize(level + 2);
+    if (may_spawn && (rc = sc->levels[level + 1].reserve((size_t)n, (size_t)J))) return rc;
+    LevelBufs nx = sc->levels[level + 1].bufs(0);
+    timer.begin(2);
+    {
+      const int blocks = std::max(1, std::min((n + 127) / 128, g_sm_count * 16));
+      k_shade<<<blocks, 128, 0, st>>>(sc->dev, fp, lv, nx, level, J, Lmax, S, nc + level, level == 0 ? d_rgba : nullptr,
+                                     level == 0 ? d_rgbf : nullptr, ctr);
+    }
+    timer.end();
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    int next_n = 0;
+    if (may_spawn) {
+      CUDA_TRY(cudaMemcpyAsync(sc->h_count, nc + level, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      next_n = sc->h_count[0];
+    }
+    if (next_n <= 0) break;
+    secondary += next_n;
+    level_n.push_back(next_n);
+  }
+  // ---- K3b: fold deepest-first ----
+  const int deepest = (int)level_n.size() - 1;
+  for (int level = deepest - 1; level >= 0; --level) {
+    LevelBufs lv = sc->levels[level].bufs(level_n[level]);
+    LevelBufs nx = sc->levels[level + 1].bufs(level_n[level + 1]);
+    timer.begin(2);
+    const int blocks = std::max(1, std::min((lv.n + 255) / 256, g_sm_count * 16));
+    k_fold<<<blocks, 256, 0, st>>>(lv, nx, level, level == 0 ? d_rgba : nullptr, level == 0 ? d_rgbf : nullptr);
+    timer.end();
+    ++launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+
+  if (want_stats) {
+    cudaEventRecord(ev_b, st);
+    CUDA_TRY(cudaMemcpyAsync(sc->h_counters, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memset(stats, 0, sizeof(*stats));
+    float cat[4] = {0, 0, 0, 0};
+    timer.collect(cat);
+    cudaEventElapsedTime(&stats->ms_total, ev_a, ev_b);
+    cudaEventDestroy(ev_a); cudaEventDestroy(ev_b);
+    stats->ms_trace = cat[0]; stats->ms_shadow = cat[1]; stats->ms_shade = cat[2];
+    stats->rays_primary = n0;
+    stats->pixels = n0;
+    stats->rays_shadow = (int64_t)sc->h_counters->shadow_rays;
+    stats->rays_secondary = secondary;
+    stats->levels = (int32_t)level_n.size();
+    stats->kernel_launches = launches;
+    stats->box_tests = (int64_t)sc->h_counters->box_tests;
+    stats->tri_tests = (int64_t)sc->h_counters->tri_tests;
+    stats->shade_samples = (int64_t)sc->h_counters->shade_samples;
+  }
+  return RT_OK;
+}
+
+}  // namespace
+
+extern "C" int rt_render_device(RtScene *sc, const RtCamera *cam, const RtLights *lights, const RtParams *p,
+                                void *d_rgba, int32_t *d_face, float *d_t, float *d_rgb_f32, void *stream,
+                                RtStats *stats) {
+  if (!sc || !cam || !lights || !p || !d_rgba) return fail(RT_ERR_INVALID, "null argument");
+  if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "bad image size %dx%d", p->width, p->height);
+  if (p->band_world > 1 && (p->band_rank < 0 || p->band_rank >= p->band_world)) return fail(RT_ERR_INVALID, "bad band rank");
+  int rc = ensure_device();
+  if (rc) return rc;
+  FrameParams fp;
+  if ((rc = fill_frame(fp, cam, lights, p))) return rc;
+  const long long n0 = (long long)fp.local_rows * fp.width;
+  if (n0 > 0x7fffffffLL / 32) return fail(RT_ERR_LIMIT, "image too large for one call (%lld pixels); shard it in bands", n0);
+  if (n0 == 0) return RT_OK;
+  return run_pipeline(sc, fp, false, (int)n0, (uchar4 *)d_rgba, d_face, d_t, d_rgb_f32, (cudaStream_t)stream, stats);
+}
+
+extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *lights, const RtParams *p, uint8_t *rgba_out,
+                         int32_t *face_out, float *t_out, float *rgb_f32_out, RtStats *stats) {
+  if (!sc || !p || !rgba_out) return fail(RT_ERR_INVALID, "null argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  const size_t n = (size_t)rt_local_rows(p) * (size_t)std::max(0, p->width);
+  if ((rc = sc->out_rgba.reserve(n * 4))) return rc;
+  if (face_out && (rc = sc->out_face.reserve(n * 4))) return rc;
+  if (t_out && (rc = sc->out_t.reserve(n * 4))) return rc;
+  if (rgb_f32_out && (rc = sc->out_rgbf.reserve(n * 12))) return rc;
+  rc = rt_render_device(sc, cam, lights, p, sc->out_rgba.p, face_out ? sc->out_face.as<int32_t>() : nullptr,
+                        t_out ? sc->out_t.as<float>() : nullptr, rgb_f32_out ? sc->out_rgbf.as<float>() : nullptr,
+                        nullptr, stats);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(rgba_out, sc->out_rgba.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  if (face_out) CUDA_TRY(cudaMemcpyAsync(face_out, sc->out_face.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  if (t_out) CUDA_TRY(cudaMemcpyAsync(t_out, sc->out_t.p, n * 4, cudaMemcpyDeviceToHost, 0));
+  if (rgb_f32_out) CUDA_TRY(cudaMemcpyAsync(rgb_f32_out, sc->out_rgbf.p, n * 12, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched per-function entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_trace_rays(RtScene *sc, int64_t n, const float *origins, const float *dirs, const RtLights *lights,
+                             const RtParams *p, float *rgb_out, int32_t *face_out, float *t_out) {
+  if (!sc || !origins || !dirs || !lights || !p || !rgb_out) return fail(RT_ERR_INVALID, "null argument");
+  if (n <= 0) return RT_OK;
+  if (n > (1 << 26)) return fail(RT_ERR_LIMIT, "at most 2^26 rays per call");
+  int rc = ensure_device();
+  if (rc) return rc;
+  FrameParams fp;
+  if ((rc = fill_frame(fp, nullptr, lights, p))) return rc;
+  fp.width = (int)n; fp.height = 1; fp.local_rows = 1; fp.band_world = 1;
+  const int Lmax = std::max(1, fp.n_lights);
+  const int S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
+  if ((int)sc->levels.size() < 1) sc->levels.resize(1);
+  if ((rc = sc->levels[0].reserve((size_t)n, (size_t)(Lmax + Lmax * S)))) return rc;
+  std::vector<float> ho((size_t)n * 4), hd((size_t)n * 4);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) { ho[4 * i + k] = origins[3 * i + k]; hd[4 * i + k] = dirs[3 * i + k]; }
+    ho[4 * i + 3] = bits(0); hd[4 * i + 3] = 0.f;
+  }
+  CUDA_TRY(cudaMemcpy(sc->levels[0].ray_o.p, ho.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(sc->levels[0].ray_d.p, hd.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(sc->levels[0].ray_l.p, 0, (size_t)n * 8));
+  if ((rc = sc->out_rgbf.reserve((size_t)n * 12))) return rc;
+  if ((rc = run_pipeline(sc, fp, true, (int)n, nullptr, nullptr, nullptr, sc->out_rgbf.as<float>(), 0, nullptr))) return rc;
+  CUDA_TRY(cudaMemcpy(rgb_out, sc->out_rgbf.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
+  if (face_out) CUDA_TRY(cudaMemcpy(face_out, sc->levels[0].hit_face.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (t_out) CUDA_TRY(cudaMemcpy(t_out, sc->levels[0].hit_t.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+extern "C" int rt_light_strikes(RtScene *sc, int64_t n, const float *hit_points, const RtLights *lights, uint8_t *visible_out) {
+  if (!sc || !hit_points || !lights || !visible_out) return fail(RT_ERR_INVALID, "null argument");
+  if (n <= 0 || lights->n <= 0) return RT_OK;
+  int rc = ensure_device();
+  if (rc) return rc;
+  RtParams p; rt_default_params(&p);
+  FrameParams fp;
+  if ((rc = fill_frame(fp, nullptr, lights, &p))) return rc;
+  if ((rc = sc->in_a.reserve((size_t)n * 12)) || (rc = sc->in_b.reserve((size_t)n * lights->n))) return rc;
+  CUDA_TRY(cudaMemcpy(sc->in_a.p, hit_points, (size_t)n * 12, cudaMemcpyHostToDevice));
+  const int64_t jobs = n * lights->n;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((jobs + 127) / 128, g_sm_count * 16));
+  k_light_strikes<<<blocks, 128>>>(sc->dev, fp, n, sc->in_a.as<float>(), sc->in_b.as<uint8_t>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(visible_out, sc->in_b.p, (size_t)jobs, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+extern "C" int rt_box_intersect(RtScene *sc, int64_t n, const float *origins, const float *dests, uint8_t *hit_out) {
+  if (!sc || !origins || !dests || !hit_out) return fail(RT_ERR_INVALID, "null argument");
+  if (n <= 0) return RT_OK;
+  int rc = ensure_device();
+  if (rc) return rc;
+  if ((rc = sc->in_a.reserve((size_t)n * 24)) || (rc = sc->in_b.reserve((size_t)n))) return rc;
+  float *d_o = sc->in_a.as<float>(), *d_d = d_o + (size_t)n * 3;
+  CUDA_TRY(cudaMemcpy(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_d, dests, (size_t)n * 12, cudaMemcpyHostToDevice));
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, g_sm_count * 16));
+  k_box_intersect<<<blocks, 256>>>(sc->dev, n, d_o, d_d, sc->in_b.as<uint8_t>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(hit_out, sc->in_b.p, (size_t)n, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+extern "C" int rt_screen_to_world(const RtCamera *cam, int64_t n, const float *pixels_xy, float *out) {
+  if (!cam || !pixels_xy || !out) return fail(RT_ERR_INVALID, "null argument");
+  if (n <= 0) return RT_OK;
+  int rc = ensure_device();
+  if (rc) return rc;
+  RtParams p; rt_default_params(&p);
+  RtLights l{}; l.n = 0; l.pos = nullptr;
+  FrameParams fp;
+  if ((rc = fill_frame(fp, cam, &l, &p))) return rc;
+  float *d_in = nullptr, *d_out = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_in, (size_t)n * 8));
+  if (cudaMalloc((void **)&d_out, (size_t)n * 12) != cudaSuccess) { cudaFree(d_in); return fail(RT_ERR_CUDA, "cudaMalloc failed"); }
+  cudaMemcpy(d_in, pixels_xy, (size_t)n * 8, cudaMemcpyHostToDevice);
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, g_sm_count * 16));
+  k_screen_to_world<<<blocks, 256>>>(fp, n, d_in, d_out);
+  cudaError_t e = cudaMemcpy(out, d_out, (size_t)n * 12, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "screen_to_world: %s", cudaGetErrorString(e));
+  return RT_OK;
+}
+
+// Host-side restatement of the light sample positions handed to the shadow kernel (the device
+// computes the same expression per job; this entry point serves Flyscene::createSpherePoint).
+extern "C" int rt_light_samples(const RtParams *p, const float light[3], float *out) {
+  if (!p || !light || !out) return fail(RT_ERR_INVALID, "null argument");
+  if (p->point_light) { out[0] = light[0]; out[1] = light[1]; out[2] = light[2]; return 1; }
+  if (!p->area_light) return fail(RT_ERR_INVALID, "spherical random light mode is not supported");
+  if (p->usteps * p->vsteps > RT_MAX_SAMPLES) return fail(RT_ERR_LIMIT, "too many samples");
+  const float ux = light[0] + p->area_len_x * 1.0f, vy = light[1] + p->area_len_y * 1.0f, uz = light[2] + p->area_len_x * 0.0f;
+  int k = 0;
+  for (int i = 0; i < p->usteps; ++i)
+    for (int j = 0; j < p->vsteps; ++j) {
+      out[3 * k] = (float)((double)i + 0.5) * (ux / (float)p->usteps);
+      out[3 * k + 1] = (float)((double)j + 0.5) * (vy / (float)p->vsteps);
+      out[3 * k + 2] = uz;
+      ++k;
+    }
+  return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// output: writePPMImage, tucano/utils/ppmIO.hpp:130-151
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_write_ppm(const char *path, const uint8_t *rgba, int32_t width, int32_t height, int32_t binary) {
+  if (!path || !rgba || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad argument");
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(RT_ERR_IO, "cannot open %s for writing", path);
+  if (binary) {
+    fprintf(f, "P6\n%d %d\n255\n", width, height);
+    std::vector<uint8_t> row((size_t)width * 3);
+    for (int j = 0; j < height; ++j) {
+      for (int i = 0; i < width; ++i) {
+        const uint8_t *px = rgba + ((size_t)j * width + i) * 4;
+        row[3 * i] = px[0]; row[3 * i + 1] = px[1]; row[3 * i + 2] = px[2];
+      }
+      fwrite(row.data(), 1, row.size(), f);
+    }
+  } else {
+    // "r g b " per pixel, newline per row, exactly the reference's text layout
+    static const char digits[] = "0123456789";
+    fprintf(f, "P3\n%d %d\n255\n", width, height);
+    std::string line;
+    line.reserve((size_t)width * 12 + 2);
+    for (int j = 0; j < height; ++j) {
+      line.clear();
+      for (int i = 0; i < width; ++i) {
+        const uint8_t *px = rgba + ((size_t)j * width + i) * 4;
+        for (int c = 0; c < 3; ++c) {
+          const unsigned v = px[c];
+          if (v >= 100) line.push_back(digits[v / 100]);
+          if (v >= 10) line.push_back(digits[(v / 10) % 10]);
+          line.push_back(digits[v % 10]);
+          line.push_back(' ');
+        }
+      }
+      line.push_back('\n');
+      fwrite(line.data(), 1, line.size(), f);
+    }
+  }
+  fclose(f);
+  return RT_OK;
+}

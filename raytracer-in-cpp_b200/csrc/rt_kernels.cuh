@@ -1,0 +1,467 @@
+// rt_kernels.cuh -- the four kernel families of the B200 render path (sm_100a).
+//
+//   K1 k_trace_nearest  persistent-thread nearest-hit wavefront kernel (ray generation fused for
+//                       primary rays)            <- raytraceScene pixel loop src/flyscene.cpp:573-598,
+//                                                   traceRay nearest hit :655-695, BoxTree::intersect
+//   K2 k_shadow         any-hit shadow rays for the gate test and every area-light grid sample
+//                                                <- lightStrikes :912-954, createSpherePoint :962-972
+//   K3 k_shade          Phong + material switch + ballot/popc ray compaction into the next bounce
+//                       queue, framebuffer write for rays that terminate at level 0
+//                                                <- phongShade :822-859, material switch :712-760
+//   K3b k_fold          folds the per-level records back to the pixel in the reference's own
+//                       evaluation order and writes the packed uchar4 framebuffer
+//                                                <- the unwinding of traceRay's recursion + ppmIO.hpp:145
+// (citations relative to /root/reference).  Compiled with -fmad=false, see rt_device.cuh.
+#pragma once
+
+#include "rt_device.cuh"
+
+namespace rtd {
+
+// record types written by K3 and consumed by K3b
+enum RecType : uint8_t {
+  REC_TERMINAL = 0,        // rec.xyz is the final colour of this ray
+  REC_MIRROR = 1,          // 0.15*P + 0.85*child                  illum 3,4   :738
+  REC_MIRROR_FRESNEL = 2,  // f * (0.15*P + 0.85*child)            illum 5     :738-743
+  REC_GLASS9 = 3,          // 0.10*P + 0.90*child                  illum 9     :718
+  REC_REFRACT6 = 4         // 0.2*P + 0.8*child                    illum 6     :754
+};
+
+struct LevelBufs {
+  float4 *ray_o;      // (o.xyz, bits(flags)), flags bit0: light list = single point lp
+  float4 *ray_d;      // (d.xyz, lp.x)
+  float2 *ray_l;      // (lp.y, lp.z)
+  float *hit_t;
+  int32_t *hit_face;  // -1: no hit
+  uint8_t *vis;       // [n][J] visibility of every shadow job
+  float4 *rec;        // (P or colour, fresnel factor)
+  int32_t *child;     // slot of the child ray in the next level, -1 if none
+  uint8_t *type;      // RecType
+  int32_t n;
+};
+
+struct Counters {
+  unsigned long long shadow_rays;
+  unsigned long long secondary_rays;
+  unsigned long long box_tests;
+  unsigned long long tri_tests;
+  unsigned long long shade_samples;
+};
+
+__device__ __forceinline__ int global_row(const FrameParams &fp, int local_row) {
+  if (fp.band_world <= 1) return local_row;
+  const int band = local_row / fp.band_rows, within = local_row - band * fp.band_rows;
+  return (band * fp.band_world + fp.band_rank) * fp.band_rows + within;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: nearest hit.  Persistent CTAs; each warp pulls 32 work items at a time from a global
+// counter.  Primary rays: one item = one pixel of an 8x4 tile (coherent warps); the ray is
+// generated in-kernel and stored to the level-0 queue for K2/K3.
+// ---------------------------------------------------------------------------------------------
+template <bool PRIMARY, bool STATS>
+__global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const FrameParams fp, const LevelBufs lv,
+                                                      const int n_items, unsigned long long *work_counter,
+                                                      int32_t *face_out, float *t_out, Counters *ctr) {
+  const int lane = threadIdx.x & 31;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  const int tiles_x = PRIMARY ? (fp.width + 7) >> 3 : 1;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(work_counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned long long)n_items) break;
+    int i;
+    bool valid;
+    V3 o, d;
+    bool tri_enabled = true;
+    if constexpr (PRIMARY) {
+      const int tile = (int)(base >> 5);
+      const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+      const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+      valid = px < fp.width && py < fp.local_rows;
+      i = py * fp.width + px;
+      o = ld3(fp.eye);
+      d = mk(0.f, 0.f, 0.f);
+      if (valid) {
+        const V3 screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
+        // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
+        // (scenes with analytic spheres -- not a reference feature -- skip this pre-cull, like rt_oracle.c)
+        tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, o, screen) || sc.n_spheres > 0;
+        d = sub(screen, o);  // :619, not normalised
+        lv.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0));
+        lv.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
+      }
+    } else {
+      i = (int)base + lane;
+      valid = i < lv.n;
+      if (valid) {
+        const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
+        o = mk(ro); d = mk(rd);
+      } else { o = mk(0, 0, 0); d = mk(0, 0, 0); }
+    }
+    if (!valid) continue;
+    // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
+    tri_enabled = tri_enabled && ref_box_intersect(sc.root_min, sc.root_max, o, add(o, d));
+    float best_t = RT_NO_HIT_T;
+    int best_id = -1;
+    if (tri_enabled || sc.n_spheres > 0) traverse<false, STATS>(sc, o, d, tri_enabled, best_t, best_id, st);
+    lv.hit_t[i] = best_t;
+    lv.hit_face[i] = best_id;
+    if (PRIMARY) {
+      if (face_out) face_out[i] = best_id;
+      if (t_out) t_out[i] = best_t;
+    }
+  }
+  if (STATS) {
+    atomicAdd(&ctr->box_tests, (unsigned long long)st.box_tests);
+    atomicAdd(&ctr->tri_tests, (unsigned long long)st.tri_tests);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// light list / sample generation shared by K2 and K3
+// ---------------------------------------------------------------------------------------------
+struct RayLights {
+  int n;        // lights visible to this ray's shading (scene lights, or the single inherited point)
+  bool single;
+  V3 lp;
+};
+__device__ __forceinline__ RayLights ray_lights(const FrameParams &fp, float4 ro, float4 rd, float2 rl) {
+  RayLights r;
+  r.single = (__float_as_int(ro.w) & 1) != 0;
+  r.n = r.single ? 1 : fp.n_lights;
+  r.lp = mk(rd.w, rl.x, rl.y);
+  return r;
+}
+__device__ __forceinline__ V3 light_pos(const FrameParams &fp, const RayLights &rl, int l) {
+  return rl.single ? rl.lp : ld3(fp.lights + 3 * l);
+}
+// arealight::getPointLights (arealight.hpp:15-25) through createAreaLight(light, 0.3, 0.15, u, v)
+// (src/flyscene.cpp:956-972): sample k = i*vsteps + j, i outer.
+__device__ __forceinline__ V3 area_sample(const FrameParams &fp, V3 c, int k) {
+  const int i = k / fp.vsteps, j = k - i * fp.vsteps;
+  const float ux = c.x + fp.area_len_x * 1.0f;  // uvec = corner + lengthX*(1,0,0)
+  const float vy = c.y + fp.area_len_y * 1.0f;  // vvec = corner + lengthY*(0,1,0)
+  const float uz = c.z + fp.area_len_x * 0.0f;
+  const float sx = (float)((double)i + 0.5) * (ux / (float)fp.usteps);
+  const float sy = (float)((double)j + 0.5) * (vy / (float)fp.vsteps);
+  return mk(sx, sy, uz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: shadow rays.  Job g = ray * J + j;  j < Lmax: gate ray towards light j (:699);
+// j >= Lmax: sample ray (light (j-Lmax)/S, sample (j-Lmax)%S) of phongShade's lightStrikes (:836).
+// In point mode the sample ray of a light IS its gate ray, so only the gate jobs exist (S = 0).
+// Rays are shot from the light sample towards the hit point, exactly like the reference
+// (origin = sample, direction = hit - sample, occluded iff some face has 1e-5 < t < 0.98).
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FrameParams fp, const LevelBufs lv,
+                                               const int J, const int Lmax, const int S,
+                                               const unsigned long long n_jobs,
+                                               unsigned long long *work_counter, Counters *ctr) {
+  const int lane = threadIdx.x & 31;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  unsigned traced = 0;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(work_counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_jobs) break;
+    const unsigned long long g = base + lane;
+    if (g >= n_jobs) continue;
+    const int i = (int)(g / (unsigned)J), j = (int)(g - (unsigned long long)i * (unsigned)J);
+    const int face = lv.hit_face[i];
+    if (face < 0) { lv.vis[g] = 0; continue; }
+    const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
+    const float2 rl2 = lv.ray_l[i];
+    const RayLights rl = ray_lights(fp, ro, rd, rl2);
+    int l;
+    V3 src;
+    if (j < Lmax) {
+      l = j;
+      if (l >= rl.n) { lv.vis[g] = 0; continue; }
+      src = light_pos(fp, rl, l);
+    } else {
+      const int s = j - Lmax;
+      l = s / S;
+      if (l >= rl.n) { lv.vis[g] = 0; continue; }
+      src = area_sample(fp, light_pos(fp, rl, l), s - l * S);
+    }
+    const V3 o = mk(ro), d = mk(rd);
+    const V3 hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
+    const V3 sd = sub(hit, src);                 // :920
+    const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);  // :924
+    bool occluded = false;
+    if (tri_enabled || sc.n_spheres > 0) {
+      float bt = RT_NO_HIT_T; int bi = -1;
+      occluded = traverse<true, STATS>(sc, src, sd, tri_enabled, bt, bi, st);
+    }
+    traced++;
+    lv.vis[g] = occluded ? 0 : 1;
+  }
+  // census: one atomic per warp
+  for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
+  if (lane == 0 && traced) atomicAdd(&ctr->shadow_rays, (unsigned long long)traced);
+  if (STATS) {
+    atomicAdd(&ctr->box_tests, (unsigned long long)st.box_tests);
+    atomicAdd(&ctr->tri_tests, (unsigned long long)st.tri_tests);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shading helpers
+// ---------------------------------------------------------------------------------------------
+struct Material {
+  V3 kd, ks;
+  float ns, ni;
+  int illum;
+};
+__device__ __forceinline__ Material load_material(const DevScene &sc, int mid) {
+  const float4 a = __ldg(sc.mats + 3 * mid), b = __ldg(sc.mats + 3 * mid + 1), c = __ldg(sc.mats + 3 * mid + 2);
+  Material m;
+  m.kd = mk(a); m.ns = a.w; m.ks = mk(b); m.ni = b.w; m.illum = __float_as_int(c.x);
+  return m;
+}
+
+// powf as the reference's libm computes it: glibc's powf is correctly rounded in all but
+// astronomically rare cases; CUDA's float powf is not (up to 4 ulp), so evaluate in double and
+// round once.  pow(0, y>0) = 0 and pow(1, y) = 1 short-cut the common cases.
+__device__ __forceinline__ float pow_ref(float x, float y) {
+  if (x == 1.0f) return 1.0f;
+  if (x == 0.0f && y > 0.0f) return 0.0f;
+  return (float)pow((double)x, (double)y);
+}
+
+// Flyscene::fresnel, src/flyscene.cpp:890-910
+__device__ __forceinline__ float fresnel_ref(V3 I, V3 N, float ior) {
+  float cosi = dot(I, N);
+  float etai = 1.f, etat = ior;
+  if (cosi > 0.f) { const float tmp = etai; etai = etat; etat = tmp; }
+  const float sint = etai / etat * sqrtf(max_std(0.f, 1.f - cosi * cosi));
+  if (sint >= 1.f) return 1.f;
+  const float cost = sqrtf(max_std(0.f, 1.f - sint * sint));
+  cosi = fabsf(cosi);
+  const float Rs = ((etat * cosi) - (etai * cost)) / ((etat * cosi) + (etai * cost));
+  const float Rp = ((etai * cosi) - (etat * cost)) / ((etai * cosi) + (etat * cost));
+  return (Rs * Rs + Rp * Rp) / 2.f;
+}
+
+// refraction vector, src/flyscene.cpp:747-749 (float c1, double pow/sqrt for c2)
+__device__ __forceinline__ V3 refract_ref(V3 d, V3 n, float ni) {
+  const float c1 = fabsf(dot(d, n));
+  const float inv = 1.f / ni;
+  const double p1 = (double)inv * (double)inv;
+  const double p2 = (double)c1 * (double)c1;
+  const float c2 = (float)sqrt(1.0 - p1 * (1.0 - p2));
+  return add(mul(inv, d), mul(inv * c1 - c2, n));
+}
+
+// ppmIO.hpp:145 : min(255, (int)(255*c)); negative / NaN results (printed as negative numbers by
+// the reference) are stored as 0 in the packed framebuffer.
+__device__ __forceinline__ unsigned char quantize(float c) {
+  const float v = 255.f * c;
+  int q = (v != v) ? 0 : __float2int_rz(v);
+  q = q < 255 ? q : 255;
+  return (unsigned char)(q < 0 ? 0 : q);
+}
+__device__ __forceinline__ uchar4 pack_pixel(V3 c) { return make_uchar4(quantize(c.x), quantize(c.y), quantize(c.z), 255); }
+
+__device__ __forceinline__ V3 blend(RecType ty, V3 P, float f, V3 child) {
+  V3 c;
+  switch (ty) {
+    case REC_MIRROR: c = add(mul(0.15f, P), mul(0.85f, child)); break;
+    case REC_MIRROR_FRESNEL: c = mul(f, add(mul(0.15f, P), mul(0.85f, child))); break;
+    case REC_GLASS9: c = add(mul(0.10f, P), mul(0.90f, child)); break;
+    case REC_REFRACT6: c = add(mul(0.2f, P), mul(0.8f, child)); break;
+    default: c = P; break;
+  }
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: shade one bounce level.  One thread per ray; warps stay converged around the queue append.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FrameParams fp, const LevelBufs lv,
+                                              const LevelBufs nx, const int level, const int J, const int Lmax,
+                                              const int S, int *next_count, uchar4 *fb, float *rgb_f32,
+                                              Counters *ctr) {
+  const int n_round = (lv.n + 31) & ~31;
+  unsigned samples_shaded = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool valid = i < lv.n;
+    bool spawn = false;
+    V3 colour = mk(1.f, 1.f, 1.f);  // BACKGROUND, src/flyscene.cpp:12
+    RecType ty = REC_TERMINAL;
+    float fres = 1.f;
+    V3 child_o = mk(0, 0, 0), child_d = mk(0, 0, 0), child_lp = mk(0, 0, 0);
+    int child_flags = 0;
+    const int face = valid ? lv.hit_face[i] : -1;
+    if (face >= 0) {
+      const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
+      const float2 rl2 = lv.ray_l[i];
+      const RayLights rl = ray_lights(fp, ro, rd, rl2);
+      const V3 o = mk(ro), d = mk(rd);
+      const V3 hit = add(o, mul(lv.hit_t[i], d));
+      const uint8_t *vis = lv.vis + (size_t)i * J;
+      bool any = false;
+      for (int l = 0; l < rl.n; ++l) any = any || (vis[l] != 0);
+      if (!any) {
+        colour = mk(0.f, 0.f, 0.f);  // SHADOW, :699-710
+      } else {
+        // ---- surface data ----
+        V3 fn, nrm_in;
+        int mid;
+        if (face < sc.n_faces) {
+          const float4 *sp = sc.shade + (size_t)face * 7;
+          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
+          const float4 s3 = __ldg(sp + 3), s4 = __ldg(sp + 4), s5 = __ldg(sp + 5), s6 = __ldg(sp + 6);
+          mid = __float_as_int(s0.w);
+          fn = mk(s6);
+          // getInterpolatedNormal, :864-888
+          const V3 a = mk(s0), b = mk(s1), c = mk(s2);
+          const V3 v0 = sub(b, a), v1 = sub(c, a), v2 = sub(hit, a);
+          const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+          const float denom = d00 * d11 - d01 * d01;
+          const float bv = (d11 * d20 - d01 * d21) / denom;
+          const float bw = (d00 * d21 - d01 * d20) / denom;
+          const float bu = 1.0f - bv - bw;
+          nrm_in = add(add(mul(bu, mk(s3)), mul(bv, mk(s4))), mul(bw, mk(s5)));
+        } else {
+          const int si = face - sc.n_faces;
+          const float4 cr = __ldg(sc.spheres + si);
+          mid = __ldg(sc.sphere_mat + si);
+          nrm_in = sub(hit, mk(cr));
+          fn = normalized(nrm_in);
+        }
+        const Material m = load_material(sc, mid);
+        // ---- phongShade, :822-859 ----
+        const V3 I = ld3(fp.light_color);
+        const V3 normal = normalized(affine_point(sc.model, nrm_in));
+        const V3 eye = normalized(mul(-1.f, sub(hit, o)));
+        const V3 Ikd = cmul(I, m.kd), Iks = cmul(I, m.ks);
+        V3 P = mk(0.f, 0.f, 0.f);
+        const int ns = fp.point_light ? 1 : S;
+        for (int l = 0; l < rl.n; ++l) {
+          float sum = 0.f;
+          V3 acc = mk(0.f, 0.f, 0.f);
+          const V3 lpos = light_pos(fp, rl, l);
+          for (int s = 0; s < ns; ++s) {
+            const bool v = fp.point_light ? (vis[l] != 0) : (vis[Lmax + l * S + s] != 0);
+            if (!v) continue;
+            sum += 1.f;
+            const V3 spos = fp.point_light ? lpos : area_sample(fp, lpos, s);
+            const V3 ldir = normalized(sub(spos, hit));
+            const float costheta = max_std(0.0f, dot(ldir, normal));
+            const V3 diffuse = mul(costheta, Ikd);
+            const V3 refl = normalized(sub(ldir, mul(2.f * dot(ldir, normal), normal)));
+            const float cosphi = max_std(0.0f, dot(eye, mul(-1.f, refl)));
+            const V3 specular = mul(pow_ref(cosphi, m.ns), Iks);
+            acc = add(acc, add(diffuse, specular));
+            samples_shaded++;
+          }
+          const float fa = sum / (float)ns, fb2 = 1.3f / (float)ns;
+          P = add(P, mul(fb2, mul(fa, acc)));
+        }
+        // ---- material switch, :712-760 ----
+        int imodel = m.illum;
+        if (fp.max_depth >= 0 && level >= fp.max_depth) imodel = 2;
+        colour = P;
+        if (imodel == 9) {
+          ty = REC_GLASS9; child_d = d;
+          child_flags = rl.single ? 1 : 0; child_lp = rl.lp;
+        } else if (imodel == 6) {
+          ty = REC_REFRACT6; child_d = refract_ref(d, fn, m.ni);
+          child_flags = rl.single ? 1 : 0; child_lp = rl.lp;
+        } else if (imodel > 2 && imodel < 6) {
+          child_d = sub(d, mul(2.f * dot(d, fn), fn));  // :734
+          ty = REC_MIRROR;
+          if (imodel == 5) { ty = REC_MIRROR_FRESNEL; fres = fresnel_ref(child_d, fn, m.ni); }
+          child_flags = 1; child_lp = hit;  // reflectedLights = { hitPoint }, :735-736
+        }
+        // illum 7: both child traces are multiplied by (1 - fresnelIndex) = 0 -> Phong (:726,751,758)
+        if (ty != REC_TERMINAL) {
+          if (level >= fp.guard_depth) {
+            // recursion guard of unbounded mode: the child returns BACKGROUND untraced
+            colour = blend(ty, P, fres, mk(1.f, 1.f, 1.f));
+            ty = REC_TERMINAL;
+          } else {
+            spawn = true; child_o = hit;
+          }
+        }
+      }
+    }
+    const int slot = warp_append(next_count, spawn);
+    if (!valid) continue;
+    if (spawn) {
+      nx.ray_o[slot] = make_float4(child_o.x, child_o.y, child_o.z, __int_as_float(child_flags));
+      nx.ray_d[slot] = make_float4(child_d.x, child_d.y, child_d.z, child_lp.x);
+      nx.ray_l[slot] = make_float2(child_lp.y, child_lp.z);
+    }
+    lv.rec[i] = make_float4(colour.x, colour.y, colour.z, fres);
+    lv.child[i] = spawn ? slot : -1;
+    lv.type[i] = (uint8_t)ty;
+    if (level == 0 && ty == REC_TERMINAL) {
+      if (fb) fb[i] = pack_pixel(colour);
+      if (rgb_f32) { rgb_f32[3 * (size_t)i] = colour.x; rgb_f32[3 * (size_t)i + 1] = colour.y; rgb_f32[3 * (size_t)i + 2] = colour.z; }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) samples_shaded += __shfl_down_sync(0xffffffffu, samples_shaded, off);
+  if ((threadIdx.x & 31) == 0 && samples_shaded) atomicAdd(&ctr->shade_samples, (unsigned long long)samples_shaded);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: fold level k from level k+1 (deepest first); level 0 writes the framebuffer.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fold(const LevelBufs lv, const LevelBufs nx, const int level, uchar4 *fb,
+                                             float *rgb_f32) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lv.n; i += gridDim.x * blockDim.x) {
+    const RecType ty = (RecType)lv.type[i];
+    if (ty == REC_TERMINAL) continue;
+    const float4 r = lv.rec[i];
+    const float4 c = nx.rec[lv.child[i]];
+    const V3 col = blend(ty, mk(r), r.w, mk(c));
+    lv.rec[i] = make_float4(col.x, col.y, col.z, 1.f);
+    if (level == 0) {
+      if (fb) fb[i] = pack_pixel(col);
+      if (rgb_f32) { rgb_f32[3 * (size_t)i] = col.x; rgb_f32[3 * (size_t)i + 1] = col.y; rgb_f32[3 * (size_t)i + 2] = col.z; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small batched entry points
+// ---------------------------------------------------------------------------------------------
+__global__ void k_box_intersect(const DevScene sc, const int64_t n, const float *o, const float *dst, uint8_t *out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ref_box_intersect(sc.root_min, sc.root_max, ld3(o + 3 * i), ld3(dst + 3 * i)) ? 1 : 0;
+}
+
+__global__ void k_screen_to_world(const FrameParams fp, const int64_t n, const float *pix, float *out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const V3 w = screen_to_world(fp, pix[2 * i], pix[2 * i + 1]);
+    out[3 * i] = w.x; out[3 * i + 1] = w.y; out[3 * i + 2] = w.z;
+  }
+}
+
+// lightStrikes for explicit hit points: job = point * L + light
+__global__ void __launch_bounds__(128) k_light_strikes(const DevScene sc, const FrameParams fp, const int64_t n,
+                                                      const float *hits, uint8_t *out) {
+  const int L = fp.n_lights;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n * L; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = g / L;
+    const int l = (int)(g - i * L);
+    const V3 hit = ld3(hits + 3 * i), src = ld3(fp.lights + 3 * l);
+    const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);
+    bool occ = false;
+    if (tri_enabled || sc.n_spheres > 0) {
+      float bt = RT_NO_HIT_T; int bi = -1;
+      occ = traverse<true, false>(sc, src, sub(hit, src), tri_enabled, bt, bi, st);
+    }
+    out[g] = occ ? 0 : 1;
+  }
+}
+
+}  // namespace rtd

@@ -1,0 +1,83 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the golden vectors produced
+by the reference itself, and against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): primary-hit face ids bit-exact (except documented float-tie /
+sliver pixels), final 8-bit RGB within +-1 LSB on >= 99.9 % of pixels, max error stated."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import GENERATED, SCENE_OF, case_params, load_golden, scene_arrays
+
+pytestmark = pytest.mark.gpu
+
+ALL_CASES = list(SCENE_OF) + list(GENERATED)
+# documented exceptions: pixels whose reference hit is a phantom hit of a degenerate (sliver) face
+# that only the reference's octree candidate lists expose
+MAX_FACE_MISMATCH = {"dodge_point_1000": 4, "dodge_area_rot_400x300": 4}
+
+
+def quant(rgb):
+    v = (np.float32(255) * rgb.astype(np.float32)).astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        q = np.trunc(np.nan_to_num(v, nan=0.0, posinf=3e9, neginf=-3e9)).astype(np.int64)
+    return np.clip(np.minimum(255, q), 0, 255)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_render_matches_reference_golden(case, pkg, capi, scene_dir):
+    g = load_golden(case)
+    verts, fn, vn, mid, mats = scene_arrays(case, pkg, scene_dir)
+    capi.init(0)
+    scene = capi.Scene(verts, fn, vn, mid, mats, g["model_matrix"])
+    cp = case_params(g)
+    cam = capi.make_camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    lights = capi.Lights(g["lights"], g["light_color"])
+    params = capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], cp["max_depth"], cp["grid"])
+    fr = scene.render(cam, lights, params)
+    px, py = g["pxy"][:, 0], g["pxy"][:, 1]
+
+    face = fr.face[py, px]
+    bad_face = int((face != g["face"]).sum())
+    assert bad_face <= MAX_FACE_MISMATCH.get(case, 0), f"{bad_face} primary-hit ids differ from the reference"
+    same = face == g["face"]
+    t = fr.t[py, px]
+    assert (t[same].view(np.uint32) == g["t"][same].view(np.uint32)).all(), "hit parameter t differs bitwise"
+
+    ref8 = quant(g["rgb"])
+    got8 = fr.rgba[py, px, :3].astype(np.int64)
+    err = np.abs(got8 - ref8).max(-1)
+    frac_ok = float((err <= 1).mean())
+    exact = float((err == 0).mean())
+    print(f"{case}: pixels {len(px)} face mismatches {bad_face} rgb8 exact {exact:.6f} within1 {frac_ok:.6f} "
+          f"max err {int(err.max())} float-rgb bit-identical {(fr.rgb[py, px].view(np.uint32) == g['rgb'].view(np.uint32)).all(-1).mean():.6f}")
+    assert frac_ok >= 0.999, f"only {frac_ok:.5f} of pixels within +-1 LSB (max err {int(err.max())})"
+    scene.close()
+
+
+@pytest.mark.parametrize("case", ["cube_area_640x360", "gallery_area_200x150", "hf32_point_256x144"])
+def test_full_frame_matches_oracle(case, pkg, capi, oracle_mod, scene_dir):
+    """Every pixel of the frame (not only the golden subset) against the CPU oracle."""
+    O = oracle_mod
+    g = load_golden(case)
+    verts, fn, vn, mid, mats = scene_arrays(case, pkg, scene_dir)
+    cp = case_params(g)
+    capi.init(0)
+    scene = capi.Scene(verts, fn, vn, mid, mats, g["model_matrix"])
+    cam = capi.make_camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    lights = capi.Lights(g["lights"], g["light_color"])
+    params = capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], cp["max_depth"], cp["grid"])
+    fr = scene.render(cam, lights, params)
+
+    orc = O.Oracle(O.BakedScene(verts, fn, vn, mid, mats, g["model_matrix"]), area=cp["area"], point=cp["point"],
+                   max_depth=cp["max_depth"], grid=cp["grid"], light_color=g["light_color"])
+    ocam = O.Oracle.camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    pxy, rgb, face, t, rgb8 = orc.render(ocam, g["lights"], cp["w"], cp["h"], stride=1, threads=8)
+    px, py = pxy[:, 0], pxy[:, 1]
+    assert (fr.face[py, px] == face).all()
+    assert (fr.t[py, px].view(np.uint32) == t.view(np.uint32)).all()
+    err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - quant(rgb)).max(-1)
+    assert (err <= 1).mean() >= 0.999, f"max err {err.max()}"
+    print(f"{case}: full frame {len(px)} px, rgb8 exact {(err == 0).mean():.6f}, max err {int(err.max())}")
+    scene.close()
