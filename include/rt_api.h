@@ -108,8 +108,10 @@ typedef struct {
   float ms_shadow;          /* any-hit kernels (K2) */
   float ms_shade;           /* shade / compaction / fold / framebuffer kernels (K3) */
   int32_t kernel_launches;  /* kernels launched by this call */
-  /* traversal work counters, filled only when rt_set_option("stats", 1) */
+  /* traversal work counters, filled only when rt_set_option("stats", 1):
+   * ray-AABB and ray-triangle tests of the nearest-hit kernels (K1) and of the shadow kernels (K2) */
   int64_t box_tests, tri_tests, shade_samples;
+  int64_t box_tests_shadow, tri_tests_shadow;
 } RtStats;
 
 typedef struct RtScene RtScene;   /* device-resident BVH + triangle soup + shading tables */

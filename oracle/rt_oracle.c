@@ -536,7 +536,9 @@ static v3 phong_shade(const OrScene *s, v3 origin, v3 hit, int face, const float
     float sum = 0;
     v3 colour = V(0, 0, 0);
     int ns = or_light_samples(&s->p, lightsp + 3 * l, samples);
-    light_strikes(s, hit, samples, ns, visible, census);
+    /* census convention (BASELINE.json north_star): in point mode the sample ray of a light is the
+     * very same query as its gate ray (:699 vs :836), so it is counted once */
+    light_strikes(s, hit, samples, ns, visible, s->p.point_light ? NULL : census);
     for (int i = 0; i < ns; ++i) {
       if (!visible[i]) continue;
       sum++;

@@ -649,6 +649,8 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
     stats->box_tests = (int64_t)sc->h_counters->box_tests;
     stats->tri_tests = (int64_t)sc->h_counters->tri_tests;
     stats->shade_samples = (int64_t)sc->h_counters->shade_samples;
+    stats->box_tests_shadow = (int64_t)sc->h_counters->box_tests_k2;
+    stats->tri_tests_shadow = (int64_t)sc->h_counters->tri_tests_k2;
   }
   return RT_OK;
 }

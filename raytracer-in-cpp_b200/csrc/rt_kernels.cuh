@@ -43,9 +43,11 @@ struct LevelBufs {
 struct Counters {
   unsigned long long shadow_rays;
   unsigned long long secondary_rays;
-  unsigned long long box_tests;
-  unsigned long long tri_tests;
-  unsigned long long shade_samples;
+  unsigned long long box_tests;      // K1 (nearest hit)
+  unsigned long long tri_tests;      // K1
+  unsigned long long shade_samples;  // K3
+  unsigned long long box_tests_k2;   // K2 (shadow)
+  unsigned long long tri_tests_k2;   // K2
 };
 
 __device__ __forceinline__ int global_row(const FrameParams &fp, int local_row) {
@@ -205,8 +207,8 @@ __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FramePa
   for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
   if (lane == 0 && traced) atomicAdd(&ctr->shadow_rays, (unsigned long long)traced);
   if (STATS) {
-    atomicAdd(&ctr->box_tests, (unsigned long long)st.box_tests);
-    atomicAdd(&ctr->tri_tests, (unsigned long long)st.tri_tests);
+    atomicAdd(&ctr->box_tests_k2, (unsigned long long)st.box_tests);
+    atomicAdd(&ctr->tri_tests_k2, (unsigned long long)st.tri_tests);
   }
 }
 
