@@ -125,7 +125,10 @@ int rt_init(int device);
 void rt_shutdown(void);
 const char *rt_last_error(void);
 int rt_device_name(char *buf, size_t n);
-/* runtime knobs: "stats" (0/1 traversal counters), "leaf_size", "persistent_ctas_per_sm" */
+/* runtime knobs: "stats" (0/1 traversal counters), "leaf_size", "persistent_ctas_per_sm",
+ * "reference_candidates" (default 1: scenes created afterwards filter BVH hits through the
+ * reference's octree candidate sets so that the image matches the reference bit for bit; 0: plain
+ * BVH = exact nearest hit over all faces) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);
 
@@ -150,6 +153,9 @@ int rt_scene_root_box(const RtScene *scene, float mn[3], float mx[3]);
 /* node / leaf / triangle counts, bytes resident on the device, build milliseconds */
 int rt_scene_info(const RtScene *scene, int64_t *n_nodes, int64_t *n_leaves, int64_t *n_tris,
                   int64_t *device_bytes, float *build_ms);
+/* Shape of the reference octree for this scene (BoxTree, capacity 1000, depth 15): out[4] =
+ * reachable leaves, inner nodes, face references, largest leaf.  Host only (no GPU needed). */
+int rt_ref_octree_stats(const RtSceneDesc *desc, int32_t capacity, int64_t out[4]);
 /* debug / test access to the flattened BVH (host copies): nodes [n_nodes][16] floats as uploaded,
  * tri_face [n_tris] original face id of each soup slot */
 int rt_scene_debug_bvh(const RtScene *scene, float *nodes, int64_t nodes_cap, int32_t *tri_face, int64_t tri_cap);

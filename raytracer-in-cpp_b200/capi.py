@@ -67,7 +67,8 @@ class RtStats(C.Structure):
 API_SYMBOLS = [
     "rt_api_version", "rt_init", "rt_shutdown", "rt_last_error", "rt_device_name", "rt_set_option",
     "rt_default_params", "rt_mesh_load_obj", "rt_mesh_desc", "rt_mesh_info", "rt_mesh_destroy",
-    "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_scene_debug_bvh",
+    "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_ref_octree_stats",
+    "rt_scene_debug_bvh",
     "rt_render", "rt_render_device", "rt_local_rows", "rt_local_row_map", "rt_trace_rays",
     "rt_light_strikes", "rt_box_intersect", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm",
 ]
@@ -102,6 +103,7 @@ def lib():
     L.rt_scene_root_box.argtypes = [vp, vp, vp]
     L.rt_scene_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rt_scene_debug_bvh.argtypes = [vp, vp, i64, vp, i64]
+    L.rt_ref_octree_stats.argtypes = [C.POINTER(RtSceneDesc), i32, vp]
     L.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp, vp, vp]
     L.rt_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp,
                                    vp, vp, vp]

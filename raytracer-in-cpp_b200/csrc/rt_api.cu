@@ -20,6 +20,7 @@
 
 #include "../host/bvh_builder.hpp"
 #include "../host/obj_loader.hpp"
+#include "../host/ref_octree.hpp"
 #include "rt_kernels.cuh"
 
 using namespace rtd;
@@ -35,6 +36,7 @@ int g_sm_count = 0;
 int g_opt_stats = 0;
 int g_opt_leaf = 4;
 int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
+int g_opt_ref_candidates = 1;
 
 int fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -77,7 +79,7 @@ struct DevBuf {
 };
 
 struct LevelStore {
-  DevBuf ray_o, ray_d, ray_l, hit_t, hit_face, vis, rec, child, type;
+  DevBuf ray_o, ray_d, ray_l, hit_t, hit_face, hit_list, vis, rec, child, type;
   int reserve(size_t n, size_t J) {
     n = std::max<size_t>(n, 1);
     int rc;
@@ -86,27 +88,26 @@ struct LevelStore {
     if ((rc = ray_l.reserve(n * 8))) return rc;
     if ((rc = hit_t.reserve(n * 4))) return rc;
     if ((rc = hit_face.reserve(n * 4))) return rc;
+    if ((rc = hit_list.reserve(n * 4))) return rc;
     if ((rc = vis.reserve(n * std::max<size_t>(J, 1)))) return rc;
     if ((rc = rec.reserve(n * 16))) return rc;
     if ((rc = child.reserve(n * 4))) return rc;
     if ((rc = type.reserve(n))) return rc;
     return RT_OK;
   }
-  LevelBufs bufs(int n) const {
+  LevelBufs bufs() const {
     LevelBufs b;
     b.ray_o = ray_o.as<float4>(); b.ray_d = ray_d.as<float4>(); b.ray_l = ray_l.as<float2>();
-    b.hit_t = hit_t.as<float>(); b.hit_face = hit_face.as<int32_t>(); b.vis = vis.as<uint8_t>();
+    b.hit_t = hit_t.as<float>(); b.hit_face = hit_face.as<int32_t>(); b.hit_list = hit_list.as<int32_t>();
+    b.vis = vis.as<uint8_t>();
     b.rec = rec.as<float4>(); b.child = child.as<int32_t>(); b.type = type.as<uint8_t>();
-    b.n = n;
     return b;
   }
   void release() {
-    ray_o.release(); ray_d.release(); ray_l.release(); hit_t.release(); hit_face.release();
+    ray_o.release(); ray_d.release(); ray_l.release(); hit_t.release(); hit_face.release(); hit_list.release();
     vis.release(); rec.release(); child.release(); type.release();
   }
 };
-
-constexpr int kMaxCounters = 512;
 
 }  // namespace
 
@@ -116,7 +117,9 @@ struct RtMesh {
 
 struct RtScene {
   DevScene dev{};
-  DevBuf nodes, prims, shade, mats, spheres, sphere_mat;
+  DevBuf nodes, prims, shade, mats, spheres, sphere_mat, oct_box, oct_face_off, oct_face_leaf;
+  int64_t oct_stats[4] = {0, 0, 0, 0};
+  float octree_ms = 0.f;
   std::vector<rt::PairNode> h_nodes;
   std::vector<int32_t> h_prim_face;
   int64_t n_leaves = 0;
@@ -124,13 +127,13 @@ struct RtScene {
   int bvh_depth = 0;
   // per-frame workspace
   std::vector<LevelStore> levels;
-  DevBuf work_counters;   // kMaxCounters x u64
-  DevBuf next_counts;     // kMaxCounters x i32
-  DevBuf counters;        // Counters
+  DevBuf frame_counts;    // FrameCounts
   DevBuf out_rgba, out_face, out_t, out_rgbf, in_a, in_b;
-  int32_t *h_count = nullptr;      // pinned
-  Counters *h_counters = nullptr;  // pinned
-  size_t device_bytes() const { return nodes.cap + prims.cap + shade.cap + mats.cap + spheres.cap + sphere_mat.cap; }
+  FrameCounts *h_counts = nullptr;  // pinned mirror
+  size_t device_bytes() const {
+    return nodes.cap + prims.cap + shade.cap + mats.cap + spheres.cap + sphere_mat.cap + oct_box.cap + oct_face_off.cap +
+           oct_face_leaf.cap;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -173,6 +176,7 @@ extern "C" int rt_set_option(const char *key, int value) {
   if (!strcmp(key, "stats")) g_opt_stats = value ? 1 : 0;
   else if (!strcmp(key, "leaf_size")) g_opt_leaf = std::max(1, std::min(16, value));
   else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
+  else if (!strcmp(key, "reference_candidates")) g_opt_ref_candidates = value ? 1 : 0;
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
 }
@@ -245,6 +249,25 @@ int upload(DevBuf &b, const void *src, size_t bytes) {
   return RT_OK;
 }
 
+int upload_octree(RtScene *sc, const rt::RefOctree &oct) {
+  const int n = oct.n_nodes();
+  std::vector<float> packed((size_t)n * 8, 0.f);
+  for (int i = 0; i < n; ++i) {
+    float *q = &packed[(size_t)i * 8];
+    const float *b = &oct.box[(size_t)i * 6];
+    q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; q[3] = bits(oct.parent[i]);
+    q[4] = b[3]; q[5] = b[4]; q[6] = b[5];
+  }
+  int rc;
+  if ((rc = upload(sc->oct_box, packed.data(), packed.size() * 4))) return rc;
+  if ((rc = upload(sc->oct_face_off, oct.face_off.data(), oct.face_off.size() * 4))) return rc;
+  if ((rc = upload(sc->oct_face_leaf, oct.face_leaf.data(), oct.face_leaf.size() * 4))) return rc;
+  sc->dev.oct_box = sc->oct_box.as<float4>();
+  sc->dev.oct_face_off = sc->oct_face_off.as<int32_t>();
+  sc->dev.oct_face_leaf = sc->oct_face_leaf.as<int32_t>();
+  return RT_OK;
+}
+
 }  // namespace
 
 extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
@@ -301,6 +324,36 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
       gmin[a] = std::min(gmin[a], boxes[T + i].mn[a]); gmax[a] = std::max(gmax[a], boxes[T + i].mx[a]);
     }
     kind[T + i] = 1;
+  }
+  // ---- reference octree as a candidate filter (host/ref_octree.hpp) ----
+  rt::RefOctree oct;
+  bool use_filter = false;
+  if (g_opt_ref_candidates && T > 0) {
+    const auto t_oct = std::chrono::high_resolution_clock::now();
+    oct = rt::build_ref_octree(desc->verts, T, 1000 /* src/flyscene.cpp:86 */, 15 /* MAX_DEPTH, src/boxTree.cpp:3 */, 0);
+    sc->octree_ms = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_oct).count();
+    sc->oct_stats[0] = oct.n_leaves; sc->oct_stats[1] = oct.n_inner; sc->oct_stats[2] = oct.n_refs; sc->oct_stats[3] = oct.max_leaf;
+    use_filter = !oct.root_is_leaf;  // a single-leaf octree offers every face whenever the root box is hit
+    if (use_filter) {
+      // Degenerate (sliver) faces: the reference's barycentric test is cancellation noise for them and
+      // reports hits far outside the triangle wherever the octree offers the face.
+      // Give such faces the union of their octree leaf boxes as BVH bounds so those phantom hits are
+      // found too; the candidate filter then decides exactly as the reference does.
+      for (int i = 0; i < T; ++i) {
+        const float *v = desc->verts + (size_t)i * 9;
+        const float e0[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]}, e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]};
+        const float d00 = hdot(e0, e0), d01 = hdot(e0, e1), d11 = hdot(e1, e1);
+        const float det = d00 * d11 - d01 * d01;
+        if (det > 1e-3f * (d00 * d11)) continue;
+        for (int k = oct.face_off[i]; k < oct.face_off[i + 1]; ++k) {
+          const float *b = &oct.box[(size_t)oct.face_leaf[k] * 6];
+          for (int a = 0; a < 3; ++a) {
+            boxes[i].mn[a] = std::min(boxes[i].mn[a], b[a]);
+            boxes[i].mx[a] = std::max(boxes[i].mx[a], b[3 + a]);
+          }
+        }
+      }
+    }
   }
   float diag = 1.f;
   if (N > 0) {
@@ -372,13 +425,12 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
       (rc = upload(sc->mats, mats.data(), mats.size() * 4)) ||
       (rc = upload(sc->spheres, desc->spheres, (size_t)S * 16)) ||
       (rc = upload(sc->sphere_mat, desc->sphere_material, (size_t)S * 4)) ||
-      (rc = sc->work_counters.reserve(kMaxCounters * 8)) || (rc = sc->next_counts.reserve(kMaxCounters * 4)) ||
-      (rc = sc->counters.reserve(sizeof(Counters)))) {
+      (use_filter && (rc = upload_octree(sc, oct))) ||
+      (rc = sc->frame_counts.reserve(sizeof(FrameCounts)))) {
     rt_scene_destroy(sc);
     return rc;
   }
-  if (cudaMallocHost((void **)&sc->h_count, kMaxCounters * sizeof(int32_t)) != cudaSuccess ||
-      cudaMallocHost((void **)&sc->h_counters, sizeof(Counters)) != cudaSuccess) {
+  if (cudaMallocHost((void **)&sc->h_counts, sizeof(FrameCounts)) != cudaSuccess) {
     rt_scene_destroy(sc);
     return fail(RT_ERR_CUDA, "cudaMallocHost failed");
   }
@@ -398,12 +450,12 @@ extern "C" void rt_scene_destroy(RtScene *sc) {
   if (!sc) return;
   sc->nodes.release(); sc->prims.release(); sc->shade.release(); sc->mats.release();
   sc->spheres.release(); sc->sphere_mat.release();
+  sc->oct_box.release(); sc->oct_face_off.release(); sc->oct_face_leaf.release();
   for (auto &l : sc->levels) l.release();
-  sc->work_counters.release(); sc->next_counts.release(); sc->counters.release();
+  sc->frame_counts.release();
   sc->out_rgba.release(); sc->out_face.release(); sc->out_t.release(); sc->out_rgbf.release();
   sc->in_a.release(); sc->in_b.release();
-  if (sc->h_count) cudaFreeHost(sc->h_count);
-  if (sc->h_counters) cudaFreeHost(sc->h_counters);
+  if (sc->h_counts) cudaFreeHost(sc->h_counts);
   delete sc;
 }
 
@@ -422,6 +474,14 @@ extern "C" int rt_scene_info(const RtScene *sc, int64_t *n_nodes, int64_t *n_lea
   if (n_tris) *n_tris = sc->dev.n_prims;
   if (device_bytes) *device_bytes = (int64_t)sc->device_bytes();
   if (build_ms) *build_ms = sc->build_ms;
+  return RT_OK;
+}
+
+extern "C" int rt_ref_octree_stats(const RtSceneDesc *desc, int32_t capacity, int64_t out[4]) {
+  if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
+  if (desc->n_faces > 0 && !desc->verts) return fail(RT_ERR_INVALID, "null verts");
+  const rt::RefOctree oct = rt::build_ref_octree(desc->verts, desc->n_faces, capacity, 15, 0);
+  out[0] = oct.n_leaves; out[1] = oct.n_inner; out[2] = oct.n_refs; out[3] = oct.max_leaf;
   return RT_OK;
 }
 
@@ -535,7 +595,15 @@ int persistent_grid(K kernel, int block) {
 }
 
 // Runs the wavefront pipeline.  Level 0 is either generated from the camera (n0 = local pixels)
-// or taken from rays already stored in level-0 queue buffers (explicit = true).
+// or taken from rays already stored in the level-0 queue buffers (explicit_rays).
+//
+// Bounded depth (max_depth >= 0, <= kAsyncDepth): every level's buffers are sized for n0 rays up
+// front and ray / hit counts stay on the device (FrameCounts), so the whole frame is one stream of
+// launches without a single host read-back.  Unbounded depth (the reference's default) cannot
+// pre-allocate 64 levels, so there the host reads the next level's ray count after each K3 and stops
+// at the first empty level.
+constexpr int kAsyncDepth = 8;
+
 int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0, uchar4 *d_rgba, int32_t *d_face,
                  float *d_t, float *d_rgbf, cudaStream_t st, RtStats *stats) {
   const bool want_stats = stats != nullptr;
@@ -547,84 +615,89 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
   const int Lmax = std::max(1, fp.n_lights);
   const int S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
   const int J = Lmax + Lmax * S;
+  if ((unsigned long long)n0 * (unsigned long long)J >= 0xffffffffull)
+    return fail(RT_ERR_LIMIT, "%d rays x %d shadow jobs exceed 2^32; render the frame in bands", n0, J);
+  const bool async = fp.max_depth >= 0 && fp.max_depth <= kAsyncDepth;
   const int depth_cap = fp.max_depth >= 0 ? fp.max_depth : fp.guard_depth;
+  if (depth_cap + 2 > RT_MAX_LEVELS) return fail(RT_ERR_LIMIT, "max_depth %d too large", fp.max_depth);
 
-  CUDA_TRY(cudaMemsetAsync(sc->work_counters.p, 0, kMaxCounters * 8, st));
-  CUDA_TRY(cudaMemsetAsync(sc->next_counts.p, 0, kMaxCounters * 4, st));
-  CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, sizeof(Counters), st));
-  unsigned long long *wc = sc->work_counters.as<unsigned long long>();
-  int *nc = sc->next_counts.as<int>();
-  Counters *ctr = sc->counters.as<Counters>();
-  int wc_used = 0, launches = 0;
+  FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
+  CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
+  int launches = 0, rc;
 
-  if ((int)sc->levels.size() < 1) sc->levels.resize(1);
-  int rc = sc->levels[0].reserve((size_t)n0, (size_t)J);
-  if (rc) return rc;
+  if (async) {
+    if ((int)sc->levels.size() < depth_cap + 2) sc->levels.resize(depth_cap + 2);
+    for (int l = 0; l <= depth_cap; ++l)
+      if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)J))) return rc;
+  } else {
+    if (sc->levels.empty()) sc->levels.resize(1);
+    if ((rc = sc->levels[0].reserve((size_t)n0, (size_t)J))) return rc;
+  }
 
-  std::vector<int> level_n;
-  level_n.push_back(n0);
-  int64_t secondary = 0;
+  static int grid_k1p = 0, grid_k1s = 0, grid_k2 = 0, grid_k1p_s = 0, grid_k1s_s = 0, grid_k2_s = 0;
+  if (!grid_k1p) {
+    grid_k1p = persistent_grid(k_trace_nearest<true, false>, 128);
+    grid_k1s = persistent_grid(k_trace_nearest<false, false>, 128);
+    grid_k2 = persistent_grid(k_shadow<false>, 128);
+    grid_k1p_s = persistent_grid(k_trace_nearest<true, true>, 128);
+    grid_k1s_s = persistent_grid(k_trace_nearest<false, true>, 128);
+    grid_k2_s = persistent_grid(k_shadow<true>, 128);
+  }
+  const int elem_blocks = std::max(1, std::min((n0 + 127) / 128, g_sm_count * 16));
 
-  const int grid_k1p = trav_stats ? persistent_grid(k_trace_nearest<true, true>, 128) : persistent_grid(k_trace_nearest<true, false>, 128);
-  const int grid_k1s = trav_stats ? persistent_grid(k_trace_nearest<false, true>, 128) : persistent_grid(k_trace_nearest<false, false>, 128);
-  const int grid_k2 = trav_stats ? persistent_grid(k_shadow<true>, 128) : persistent_grid(k_shadow<false>, 128);
-
-  for (int level = 0;; ++level) {
-    const int n = level_n[level];
-    LevelBufs lv = sc->levels[level].bufs(n);
-    if (wc_used + 2 >= kMaxCounters) return fail(RT_ERR_LIMIT, "too many bounce levels");
+  int levels_run = 0;
+  int cur_n = n0;  // host knowledge of the level's ray count (exact in sync mode, upper bound in async mode)
+  for (int level = 0; level <= depth_cap; ++level) {
+    LevelBufs lv = sc->levels[level].bufs();
+    const int n_param = level == 0 ? n0 : -1;
     // ---- K1 ----
     timer.begin(0);
     if (level == 0 && !explicit_rays) {
-      const int tiles = ((fp.width + 7) / 8) * ((fp.local_rows + 3) / 4);
-      const int items = tiles * 32;
-      if (trav_stats) k_trace_nearest<true, true><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, items, wc + wc_used, d_face, d_t, ctr);
-      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, items, wc + wc_used, d_face, d_t, ctr);
+      if (trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf);
+      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf);
     } else {
-      if (trav_stats) k_trace_nearest<false, true><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, n, wc + wc_used, nullptr, nullptr, ctr);
-      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, n, wc + wc_used, nullptr, nullptr, ctr);
+      uchar4 *fb0 = level == 0 ? d_rgba : nullptr;
+      float *rgbf0 = level == 0 ? d_rgbf : nullptr;
+      int32_t *face0 = level == 0 ? d_face : nullptr;
+      float *t0 = level == 0 ? d_t : nullptr;
+      if (trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0);
+      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0);
     }
     timer.end();
-    ++wc_used; ++launches;
     // ---- K2 ----
     timer.begin(1);
-    const unsigned long long jobs = (unsigned long long)n * (unsigned)J;
-    if (trav_stats) k_shadow<true><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, J, Lmax, S, jobs, wc + wc_used, ctr);
-    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, J, Lmax, S, jobs, wc + wc_used, ctr);
+    if (trav_stats) k_shadow<true><<<grid_k2_s, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc);
+    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc);
     timer.end();
-    ++wc_used; ++launches;
     // ---- K3 ----
     const bool may_spawn = level < depth_cap;
-    if ((int)sc->levels.size() < level + 2) sc->levels.resize(level + 2);
-    if (may_spawn && (rc = sc->levels[level + 1].reserve((size_t)n, (size_t)J))) return rc;
-    LevelBufs nx = sc->levels[level + 1].bufs(0);
+    if (!async) {
+      if ((int)sc->levels.size() < level + 2) sc->levels.resize(level + 2);
+      if (may_spawn && (rc = sc->levels[level + 1].reserve((size_t)cur_n, (size_t)J))) return rc;
+    }
+    LevelBufs nx = sc->levels[std::min(level + 1, (int)sc->levels.size() - 1)].bufs();
     timer.begin(2);
-    {
-      const int blocks = std::max(1, std::min((n + 127) / 128, g_sm_count * 16));
-      k_shade<<<blocks, 128, 0, st>>>(sc->dev, fp, lv, nx, level, J, Lmax, S, nc + level, level == 0 ? d_rgba : nullptr,
-                                     level == 0 ? d_rgbf : nullptr, ctr);
-    }
+    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fp, lv, nx, level, J, Lmax, S, fc, level == 0 ? d_rgba : nullptr,
+                                         level == 0 ? d_rgbf : nullptr);
     timer.end();
-    ++launches;
+    launches += 3;
+    levels_run = level + 1;
     CUDA_TRY(cudaGetLastError());
-    int next_n = 0;
-    if (may_spawn) {
-      CUDA_TRY(cudaMemcpyAsync(sc->h_count, nc + level, 4, cudaMemcpyDeviceToHost, st));
+    if (!may_spawn) break;
+    if (!async) {
+      CUDA_TRY(cudaMemcpyAsync(&sc->h_counts->n_rays[level + 1], &fc->n_rays[level + 1], 4, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
-      next_n = sc->h_count[0];
+      cur_n = sc->h_counts->n_rays[level + 1];
+      if (cur_n <= 0) break;
     }
-    if (next_n <= 0) break;
-    secondary += next_n;
-    level_n.push_back(next_n);
   }
   // ---- K3b: fold deepest-first ----
-  const int deepest = (int)level_n.size() - 1;
-  for (int level = deepest - 1; level >= 0; --level) {
-    LevelBufs lv = sc->levels[level].bufs(level_n[level]);
-    LevelBufs nx = sc->levels[level + 1].bufs(level_n[level + 1]);
+  for (int level = levels_run - 2; level >= 0; --level) {
+    LevelBufs lv = sc->levels[level].bufs();
+    LevelBufs nx = sc->levels[level + 1].bufs();
     timer.begin(2);
-    const int blocks = std::max(1, std::min((lv.n + 255) / 256, g_sm_count * 16));
-    k_fold<<<blocks, 256, 0, st>>>(lv, nx, level, level == 0 ? d_rgba : nullptr, level == 0 ? d_rgbf : nullptr);
+    k_fold<<<elem_blocks, 256, 0, st>>>(lv, nx, level, level == 0 ? n0 : -1, fc, level == 0 ? d_rgba : nullptr,
+                                        level == 0 ? d_rgbf : nullptr);
     timer.end();
     ++launches;
   }
@@ -632,25 +705,29 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
 
   if (want_stats) {
     cudaEventRecord(ev_b, st);
-    CUDA_TRY(cudaMemcpyAsync(sc->h_counters, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(sc->h_counts, fc, sizeof(FrameCounts), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     memset(stats, 0, sizeof(*stats));
     float cat[4] = {0, 0, 0, 0};
     timer.collect(cat);
     cudaEventElapsedTime(&stats->ms_total, ev_a, ev_b);
     cudaEventDestroy(ev_a); cudaEventDestroy(ev_b);
+    const FrameCounts &h = *sc->h_counts;
     stats->ms_trace = cat[0]; stats->ms_shadow = cat[1]; stats->ms_shade = cat[2];
     stats->rays_primary = n0;
     stats->pixels = n0;
-    stats->rays_shadow = (int64_t)sc->h_counters->shadow_rays;
+    stats->rays_shadow = (int64_t)h.ctr.shadow_rays;
+    int64_t secondary = 0;
+    int lv_used = 1;
+    for (int l = 1; l < RT_MAX_LEVELS; ++l) { secondary += h.n_rays[l]; if (h.n_rays[l] > 0) lv_used = l + 1; }
     stats->rays_secondary = secondary;
-    stats->levels = (int32_t)level_n.size();
+    stats->levels = lv_used;
     stats->kernel_launches = launches;
-    stats->box_tests = (int64_t)sc->h_counters->box_tests;
-    stats->tri_tests = (int64_t)sc->h_counters->tri_tests;
-    stats->shade_samples = (int64_t)sc->h_counters->shade_samples;
-    stats->box_tests_shadow = (int64_t)sc->h_counters->box_tests_k2;
-    stats->tri_tests_shadow = (int64_t)sc->h_counters->tri_tests_k2;
+    stats->box_tests = (int64_t)h.ctr.box_tests;
+    stats->tri_tests = (int64_t)h.ctr.tri_tests;
+    stats->shade_samples = (int64_t)h.ctr.shade_samples;
+    stats->box_tests_shadow = (int64_t)h.ctr.box_tests_k2;
+    stats->tri_tests_shadow = (int64_t)h.ctr.tri_tests_k2;
   }
   return RT_OK;
 }
@@ -720,11 +797,16 @@ extern "C" int rt_trace_rays(RtScene *sc, int64_t n, const float *origins, const
   CUDA_TRY(cudaMemcpy(sc->levels[0].ray_o.p, ho.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(sc->levels[0].ray_d.p, hd.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(sc->levels[0].ray_l.p, 0, (size_t)n * 8));
-  if ((rc = sc->out_rgbf.reserve((size_t)n * 12))) return rc;
-  if ((rc = run_pipeline(sc, fp, true, (int)n, nullptr, nullptr, nullptr, sc->out_rgbf.as<float>(), 0, nullptr))) return rc;
+  if ((rc = sc->out_rgbf.reserve((size_t)n * 12)) || (rc = sc->out_face.reserve((size_t)n * 4)) ||
+      (rc = sc->out_t.reserve((size_t)n * 4)))
+    return rc;
+  if ((rc = run_pipeline(sc, fp, true, (int)n, nullptr, sc->out_face.as<int32_t>(), sc->out_t.as<float>(),
+                         sc->out_rgbf.as<float>(), 0, nullptr)))
+    return rc;
+  CUDA_TRY(cudaStreamSynchronize(0));
   CUDA_TRY(cudaMemcpy(rgb_out, sc->out_rgbf.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
-  if (face_out) CUDA_TRY(cudaMemcpy(face_out, sc->levels[0].hit_face.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  if (t_out) CUDA_TRY(cudaMemcpy(t_out, sc->levels[0].hit_t.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (face_out) CUDA_TRY(cudaMemcpy(face_out, sc->out_face.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (t_out) CUDA_TRY(cudaMemcpy(t_out, sc->out_t.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return RT_OK;
 }
 

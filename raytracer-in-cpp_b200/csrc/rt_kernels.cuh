@@ -27,17 +27,19 @@ enum RecType : uint8_t {
   REC_REFRACT6 = 4         // 0.2*P + 0.8*child                    illum 6     :754
 };
 
+#define RT_MAX_LEVELS 68  // guard depth 64 + slack
+
 struct LevelBufs {
   float4 *ray_o;      // (o.xyz, bits(flags)), flags bit0: light list = single point lp
   float4 *ray_d;      // (d.xyz, lp.x)
   float2 *ray_l;      // (lp.y, lp.z)
   float *hit_t;
   int32_t *hit_face;  // -1: no hit
-  uint8_t *vis;       // [n][J] visibility of every shadow job
+  int32_t *hit_list;  // compacted indices of the rays that hit something (K1 -> K2, K3)
+  uint8_t *vis;       // [hit slot][J] visibility of every shadow job
   float4 *rec;        // (P or colour, fresnel factor)
   int32_t *child;     // slot of the child ray in the next level, -1 if none
   uint8_t *type;      // RecType
-  int32_t n;
 };
 
 struct Counters {
@@ -50,6 +52,16 @@ struct Counters {
   unsigned long long tri_tests_k2;   // K2
 };
 
+// Device-resident per-frame state, zeroed by one memset at frame start.  Ray and hit counts of every
+// bounce level live here, so no kernel launch depends on a host read-back.
+struct FrameCounts {
+  unsigned long long work_k1[RT_MAX_LEVELS];  // persistent-kernel work cursors
+  unsigned long long work_k2[RT_MAX_LEVELS];
+  int32_t n_rays[RT_MAX_LEVELS];              // rays queued at level k (k >= 1; level 0 comes as a parameter)
+  int32_t n_hits[RT_MAX_LEVELS];              // rays of level k that hit a primitive
+  Counters ctr;
+};
+
 __device__ __forceinline__ int global_row(const FrameParams &fp, int local_row) {
   if (fp.band_world <= 1) return local_row;
   const int band = local_row / fp.band_rows, within = local_row - band * fp.band_rows;
@@ -57,20 +69,25 @@ __device__ __forceinline__ int global_row(const FrameParams &fp, int local_row) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: nearest hit.  Persistent CTAs; each warp pulls 32 work items at a time from a global
-// counter.  Primary rays: one item = one pixel of an 8x4 tile (coherent warps); the ray is
-// generated in-kernel and stored to the level-0 queue for K2/K3.
+// K1: nearest hit.  Persistent CTAs; each warp pulls 32 work items at a time from a global cursor.
+// Primary rays: one item = one pixel of an 8x4 tile (coherent warps); the ray is generated
+// in-kernel and stored to the level-0 queue.  Rays that miss are finished here (BACKGROUND record,
+// level-0 pixel written); rays that hit are compacted into hit_list with one atomic per warp.
+// n0 >= 0: item count given by the host (level 0); n0 < 0: read fc->n_rays[level].
 // ---------------------------------------------------------------------------------------------
 template <bool PRIMARY, bool STATS>
 __global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const FrameParams fp, const LevelBufs lv,
-                                                      const int n_items, unsigned long long *work_counter,
-                                                      int32_t *face_out, float *t_out, Counters *ctr) {
+                                                      const int level, const int n0, FrameCounts *fc,
+                                                      int32_t *face_out, float *t_out, uchar4 *fb, float *rgb_f32) {
   const int lane = threadIdx.x & 31;
   TravStats st; st.box_tests = 0; st.tri_tests = 0;
   const int tiles_x = PRIMARY ? (fp.width + 7) >> 3 : 1;
+  const int n = n0 >= 0 ? n0 : fc->n_rays[level];
+  const int n_items = PRIMARY ? tiles_x * ((fp.local_rows + 3) >> 2) * 32 : n;
+  unsigned long long *cursor = &fc->work_k1[level];
   for (;;) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(work_counter, 32ull);
+    if (lane == 0) base = atomicAdd(cursor, 32ull);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= (unsigned long long)n_items) break;
     int i;
@@ -91,33 +108,51 @@ __global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const 
         // (scenes with analytic spheres -- not a reference feature -- skip this pre-cull, like rt_oracle.c)
         tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, o, screen) || sc.n_spheres > 0;
         d = sub(screen, o);  // :619, not normalised
-        lv.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0));
-        lv.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
       }
     } else {
       i = (int)base + lane;
-      valid = i < lv.n;
+      valid = i < n;
       if (valid) {
         const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
         o = mk(ro); d = mk(rd);
       } else { o = mk(0, 0, 0); d = mk(0, 0, 0); }
     }
-    if (!valid) continue;
-    // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
-    tri_enabled = tri_enabled && ref_box_intersect(sc.root_min, sc.root_max, o, add(o, d));
     float best_t = RT_NO_HIT_T;
     int best_id = -1;
-    if (tri_enabled || sc.n_spheres > 0) traverse<false, STATS>(sc, o, d, tri_enabled, best_t, best_id, st);
-    lv.hit_t[i] = best_t;
-    lv.hit_face[i] = best_id;
-    if (PRIMARY) {
+    if (valid) {
+      // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
+      const V3 dest = add(o, d);
+      tri_enabled = tri_enabled && ref_box_intersect(sc.root_min, sc.root_max, o, dest);
+      if (tri_enabled || sc.n_spheres > 0) traverse<false, STATS>(sc, o, d, dest, tri_enabled, best_t, best_id, st);
+    }
+    const bool hit = valid && best_id >= 0;
+    const int slot = warp_append(&fc->n_hits[level], hit);
+    if (!valid) continue;
+    if (hit) {
+      if (PRIMARY) {
+        lv.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0));
+        lv.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
+      }
+      lv.hit_t[i] = best_t;
+      lv.hit_face[i] = best_id;
+      lv.hit_list[slot] = i;
+    } else {
+      // BACKGROUND, src/flyscene.cpp:658-665 / :684-691
+      lv.rec[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+      lv.type[i] = (uint8_t)REC_TERMINAL;
+      if (level == 0) {
+        if (fb) fb[i] = make_uchar4(255, 255, 255, 255);
+        if (rgb_f32) { rgb_f32[3 * (size_t)i] = 1.f; rgb_f32[3 * (size_t)i + 1] = 1.f; rgb_f32[3 * (size_t)i + 2] = 1.f; }
+      }
+    }
+    if (level == 0) {
       if (face_out) face_out[i] = best_id;
       if (t_out) t_out[i] = best_t;
     }
   }
   if (STATS) {
-    atomicAdd(&ctr->box_tests, (unsigned long long)st.box_tests);
-    atomicAdd(&ctr->tri_tests, (unsigned long long)st.tri_tests);
+    atomicAdd(&fc->ctr.box_tests, (unsigned long long)st.box_tests);
+    atomicAdd(&fc->ctr.tri_tests, (unsigned long long)st.tri_tests);
   }
 }
 
@@ -152,63 +187,73 @@ __device__ __forceinline__ V3 area_sample(const FrameParams &fp, V3 c, int k) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: shadow rays.  Job g = ray * J + j;  j < Lmax: gate ray towards light j (:699);
-// j >= Lmax: sample ray (light (j-Lmax)/S, sample (j-Lmax)%S) of phongShade's lightStrikes (:836).
-// In point mode the sample ray of a light IS its gate ray, so only the gate jobs exist (S = 0).
+// K2: shadow rays for the rays of hit_list.  Job g = slot * J + j;  j < Lmax: gate ray towards light j
+// (:699);  j >= Lmax: sample ray (light (j-Lmax)/S, sample (j-Lmax)%S) of phongShade's lightStrikes
+// (:836).  In point mode the sample ray of a light IS its gate ray, so only the gate jobs exist.
 // Rays are shot from the light sample towards the hit point, exactly like the reference
 // (origin = sample, direction = hit - sample, occluded iff some face has 1e-5 < t < 0.98).
+// Each warp takes 4 x 32 jobs per cursor update to keep the atomic off the critical path.
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FrameParams fp, const LevelBufs lv,
-                                               const int J, const int Lmax, const int S,
-                                               const unsigned long long n_jobs,
-                                               unsigned long long *work_counter, Counters *ctr) {
+                                               const int level, const int J, const int Lmax, const int S,
+                                               FrameCounts *fc) {
   const int lane = threadIdx.x & 31;
   TravStats st; st.box_tests = 0; st.tri_tests = 0;
   unsigned traced = 0;
+  const unsigned n_jobs = (unsigned)fc->n_hits[level] * (unsigned)J;
+  unsigned long long *cursor = &fc->work_k2[level];
+  // grain: 4 x 32 jobs per cursor update when there is plenty of work (keeps the single-address
+  // atomic off the critical path), 32 when the job count is small (load balance over all warps)
+  const unsigned warps_total = gridDim.x * (blockDim.x >> 5);
+  const int reps = (n_jobs >= warps_total * 32u * 16u) ? 4 : 1;
   for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(work_counter, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n_jobs) break;
-    const unsigned long long g = base + lane;
-    if (g >= n_jobs) continue;
-    const int i = (int)(g / (unsigned)J), j = (int)(g - (unsigned long long)i * (unsigned)J);
-    const int face = lv.hit_face[i];
-    if (face < 0) { lv.vis[g] = 0; continue; }
-    const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
-    const float2 rl2 = lv.ray_l[i];
-    const RayLights rl = ray_lights(fp, ro, rd, rl2);
-    int l;
-    V3 src;
-    if (j < Lmax) {
-      l = j;
-      if (l >= rl.n) { lv.vis[g] = 0; continue; }
-      src = light_pos(fp, rl, l);
-    } else {
-      const int s = j - Lmax;
-      l = s / S;
-      if (l >= rl.n) { lv.vis[g] = 0; continue; }
-      src = area_sample(fp, light_pos(fp, rl, l), s - l * S);
+    unsigned long long base64 = 0;
+    if (lane == 0) base64 = atomicAdd(cursor, (unsigned long long)(32 * reps));
+    base64 = __shfl_sync(0xffffffffu, base64, 0);
+    if (base64 >= (unsigned long long)n_jobs) break;
+    const unsigned base = (unsigned)base64;
+#pragma unroll 1
+    for (int rep = 0; rep < reps; ++rep) {
+      const unsigned g = base + (unsigned)rep * 32u + (unsigned)lane;
+      if (g >= n_jobs) break;
+      const unsigned slot = g / (unsigned)J;
+      const int j = (int)(g - slot * (unsigned)J);
+      const int i = lv.hit_list[slot];
+      const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
+      const float2 rl2 = lv.ray_l[i];
+      const RayLights rl = ray_lights(fp, ro, rd, rl2);
+      int l;
+      V3 src;
+      if (j < Lmax) {
+        l = j;
+        if (l >= rl.n) { lv.vis[g] = 0; continue; }
+        src = light_pos(fp, rl, l);
+      } else {
+        const int s = j - Lmax;
+        l = s / S;
+        if (l >= rl.n) { lv.vis[g] = 0; continue; }
+        src = area_sample(fp, light_pos(fp, rl, l), s - l * S);
+      }
+      const V3 o = mk(ro), d = mk(rd);
+      const V3 hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
+      const V3 sd = sub(hit, src);                 // :920
+      const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);  // :924
+      bool occluded = false;
+      if (tri_enabled || sc.n_spheres > 0) {
+        float bt = RT_NO_HIT_T; int bi = -1;
+        occluded = traverse<true, STATS>(sc, src, sd, hit, tri_enabled, bt, bi, st);
+      }
+      traced++;
+      lv.vis[g] = occluded ? 0 : 1;
     }
-    const V3 o = mk(ro), d = mk(rd);
-    const V3 hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
-    const V3 sd = sub(hit, src);                 // :920
-    const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);  // :924
-    bool occluded = false;
-    if (tri_enabled || sc.n_spheres > 0) {
-      float bt = RT_NO_HIT_T; int bi = -1;
-      occluded = traverse<true, STATS>(sc, src, sd, tri_enabled, bt, bi, st);
-    }
-    traced++;
-    lv.vis[g] = occluded ? 0 : 1;
   }
   // census: one atomic per warp
   for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
-  if (lane == 0 && traced) atomicAdd(&ctr->shadow_rays, (unsigned long long)traced);
+  if (lane == 0 && traced) atomicAdd(&fc->ctr.shadow_rays, (unsigned long long)traced);
   if (STATS) {
-    atomicAdd(&ctr->box_tests_k2, (unsigned long long)st.box_tests);
-    atomicAdd(&ctr->tri_tests_k2, (unsigned long long)st.tri_tests);
+    atomicAdd(&fc->ctr.box_tests_k2, (unsigned long long)st.box_tests);
+    atomicAdd(&fc->ctr.tri_tests_k2, (unsigned long long)st.tri_tests);
   }
 }
 
@@ -283,16 +328,18 @@ __device__ __forceinline__ V3 blend(RecType ty, V3 P, float f, V3 child) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: shade one bounce level.  One thread per ray; warps stay converged around the queue append.
+// K3: shade one bounce level.  One thread per ray that hit (hit_list slot); warps stay converged
+// around the queue append (ballot + popc, one atomic per warp).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FrameParams fp, const LevelBufs lv,
                                               const LevelBufs nx, const int level, const int J, const int Lmax,
-                                              const int S, int *next_count, uchar4 *fb, float *rgb_f32,
-                                              Counters *ctr) {
-  const int n_round = (lv.n + 31) & ~31;
+                                              const int S, FrameCounts *fc, uchar4 *fb, float *rgb_f32) {
+  const int n_hits = fc->n_hits[level];
+  const int n_round = (n_hits + 31) & ~31;
   unsigned samples_shaded = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-    const bool valid = i < lv.n;
+  for (int slot_in = blockIdx.x * blockDim.x + threadIdx.x; slot_in < n_round; slot_in += gridDim.x * blockDim.x) {
+    const bool valid = slot_in < n_hits;
+    const int i = valid ? lv.hit_list[slot_in] : 0;
     bool spawn = false;
     V3 colour = mk(1.f, 1.f, 1.f);  // BACKGROUND, src/flyscene.cpp:12
     RecType ty = REC_TERMINAL;
@@ -306,7 +353,7 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
       const RayLights rl = ray_lights(fp, ro, rd, rl2);
       const V3 o = mk(ro), d = mk(rd);
       const V3 hit = add(o, mul(lv.hit_t[i], d));
-      const uint8_t *vis = lv.vis + (size_t)i * J;
+      const uint8_t *vis = lv.vis + (size_t)slot_in * J;
       bool any = false;
       for (int l = 0; l < rl.n; ++l) any = any || (vis[l] != 0);
       if (!any) {
@@ -394,7 +441,7 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
         }
       }
     }
-    const int slot = warp_append(next_count, spawn);
+    const int slot = warp_append(&fc->n_rays[level + 1], spawn);
     if (!valid) continue;
     if (spawn) {
       nx.ray_o[slot] = make_float4(child_o.x, child_o.y, child_o.z, __int_as_float(child_flags));
@@ -410,15 +457,17 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
     }
   }
   for (int off = 16; off > 0; off >>= 1) samples_shaded += __shfl_down_sync(0xffffffffu, samples_shaded, off);
-  if ((threadIdx.x & 31) == 0 && samples_shaded) atomicAdd(&ctr->shade_samples, (unsigned long long)samples_shaded);
+  if ((threadIdx.x & 31) == 0 && samples_shaded) atomicAdd(&fc->ctr.shade_samples, (unsigned long long)samples_shaded);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3b: fold level k from level k+1 (deepest first); level 0 writes the framebuffer.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fold(const LevelBufs lv, const LevelBufs nx, const int level, uchar4 *fb,
-                                             float *rgb_f32) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lv.n; i += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) k_fold(const LevelBufs lv, const LevelBufs nx, const int level, const int n0,
+                                             const FrameCounts *fc, uchar4 *fb, float *rgb_f32) {
+  const int n = n0 >= 0 ? n0 : fc->n_rays[level];
+  if (fc->n_rays[level + 1] == 0) return;  // nothing was spawned below this level
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const RecType ty = (RecType)lv.type[i];
     if (ty == REC_TERMINAL) continue;
     const float4 r = lv.rec[i];
@@ -460,7 +509,7 @@ __global__ void __launch_bounds__(128) k_light_strikes(const DevScene sc, const 
     bool occ = false;
     if (tri_enabled || sc.n_spheres > 0) {
       float bt = RT_NO_HIT_T; int bi = -1;
-      occ = traverse<true, false>(sc, src, sub(hit, src), tri_enabled, bt, bi, st);
+      occ = traverse<true, false>(sc, src, sub(hit, src), hit, tri_enabled, bt, bi, st);
     }
     out[g] = occ ? 0 : 1;
   }

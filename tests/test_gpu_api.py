@@ -1,0 +1,174 @@
+"""GPU tests of the batched per-function entry points of the C ABI against the oracle, of band
+sharding (multi-GPU partitioning on one device) and of size-independent properties at full size."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import case_params, load_golden, scene_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(case, pkg, O, scene_dir, **okw):
+    g = load_golden(case)
+    arrs = scene_arrays(case, pkg, scene_dir)
+    cp = case_params(g)
+    capi = pkg.capi
+    capi.init(0)
+    scene = capi.Scene(*arrs, g["model_matrix"])
+    orc = O.Oracle(O.BakedScene(*arrs, g["model_matrix"]), area=cp["area"], point=cp["point"], max_depth=cp["max_depth"],
+                   grid=cp["grid"], light_color=g["light_color"], **okw)
+    return g, cp, scene, orc
+
+
+def test_box_intersect_matches_reference_semantics(pkg, oracle_mod, scene_dir):
+    O = oracle_mod
+    g, cp, scene, orc = _setup("cube_point_1000", pkg, O, scene_dir)
+    rng = np.random.default_rng(7)
+    n = 20000
+    o = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    d = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    # edge cases: zero direction components (inf / NaN paths), origin on the box planes
+    d[:500, 0] = 0; d[500:1000, 1] = 0; d[1000:1500] = 0
+    o[1500:2000, 0] = g["root_min"][0]; d[1500:2000, 0] = 0
+    dest = (o + d).astype(np.float32)
+    got = scene.box_intersect(o, dest)
+    mn, mx = scene.root_box()
+    assert (mn == g["root_min"]).all() and (mx == g["root_max"]).all()
+    exp = np.array([O.lib().or_box_intersect(mn.ctypes.data, mx.ctypes.data, o[i].ctypes.data, dest[i].ctypes.data)
+                    for i in range(n)], np.uint8)
+    assert (got == exp).all()
+
+
+def test_screen_to_world_bit_exact(pkg, oracle_mod):
+    O = oracle_mod
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("cube_rot_500x400")  # rotated + translated camera
+    cam = capi.make_camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    ocam = O.Oracle.camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    xs, ys = np.meshgrid(np.arange(0, 500, 7), np.arange(0, 400, 5))
+    pix = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.float32)
+    got = capi.screen_to_world(cam, pix)
+    exp = np.zeros_like(got)
+    for k in range(len(pix)):
+        O.lib().or_screen_to_world(ocam, float(pix[k, 0]), float(pix[k, 1]), exp[k].ctypes.data)
+    assert (got.view(np.uint32) == exp.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("case", ["gallery_area_200x150", "dodge_point_1000"])
+def test_trace_rays_arbitrary_rays(case, pkg, oracle_mod, scene_dir):
+    """Flyscene::traceRay for rays that do not come from the camera (incoherent origins/directions)."""
+    O = oracle_mod
+    g, cp, scene, orc = _setup(case, pkg, O, scene_dir)
+    rng = np.random.default_rng(11)
+    n = 4000
+    o = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    tgt = rng.uniform(-0.6, 0.6, (n, 3)).astype(np.float32)
+    d = ((tgt - o) * rng.uniform(0.2, 3.0, (n, 1))).astype(np.float32)
+    lights = pkg.capi.Lights(g["lights"], g["light_color"])
+    params = pkg.capi.make_params(8, 8, cp["area"], cp["point"], cp["max_depth"], cp["grid"])
+    rgb, face, t = scene.trace_rays(o, d, lights, params)
+    L = np.ascontiguousarray(g["lights"], np.float32)
+    e_rgb = np.zeros((n, 3), np.float32); e_face = np.zeros(n, np.int32); e_t = np.zeros(n, np.float32)
+    for k in range(n):
+        O.lib().or_trace_ray(orc.handle, o[k].ctypes.data, d[k].ctypes.data, 0, L.ctypes.data, L.shape[0],
+                             e_rgb[k].ctypes.data, e_face[k:].ctypes.data, e_t[k:].ctypes.data)
+    assert (face == e_face).all()
+    assert (t.view(np.uint32) == e_t.view(np.uint32)).all()
+    same = (rgb.view(np.uint32) == e_rgb.view(np.uint32)).all(1)
+    close = np.isclose(rgb, e_rgb, rtol=1e-5, atol=1e-6, equal_nan=True).all(1)
+    assert close.all(), f"{(~close).sum()} rays differ"
+    print(f"{case}: {n} arbitrary rays, float RGB bit-identical for {same.mean():.5f}")
+
+
+def test_light_strikes(pkg, oracle_mod, scene_dir):
+    O = oracle_mod
+    g, cp, scene, orc = _setup("gallery_area_200x150", pkg, O, scene_dir)
+    rng = np.random.default_rng(3)
+    n = 5000
+    hits = rng.uniform(-0.7, 0.7, (n, 3)).astype(np.float32)
+    lights_np = np.array([[-1, 1.2, 1.5], [1.5, 1.0, 1.0], [0.0, 0.1, 0.2]], np.float32)
+    got = scene.light_strikes(hits, pkg.capi.Lights(lights_np))
+    exp = np.zeros((n, 3), np.uint8)
+    for k in range(n):
+        O.lib().or_light_strikes(orc.handle, hits[k].ctypes.data, lights_np.ctypes.data, 3, exp[k].ctypes.data)
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_band_sharded_render_equals_full_frame(world, pkg, scene_dir):
+    """Multi-GPU partitioning, emulated on one device: the interleaved row bands rendered by each
+    'rank' stitch to exactly the single-GPU frame (pixels are independent)."""
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("gallery_area_200x150")
+    arrs = scene_arrays("gallery_area_200x150", pkg, scene_dir)
+    scene = capi.Scene(*arrs)
+    W, H = 160, 101  # odd height: the last band is partial
+    cam = capi.default_camera(W, H)
+    lights = capi.Lights(g["lights"])
+    full = scene.render(cam, lights, capi.make_params(W, H, 1, 0, 2, (3, 3)))
+    stitched = np.zeros_like(full.rgba)
+    faces = np.full((H, W), -2, np.int32)
+    for r in range(world):
+        p = capi.make_params(W, H, 1, 0, 2, (3, 3), band_rows=8, band_rank=r, band_world=world)
+        part = scene.render(cam, lights, p)
+        rows = capi.local_row_map(p)
+        assert part.rgba.shape[0] == len(rows)
+        stitched[rows] = part.rgba
+        faces[rows] = part.face
+    assert (stitched == full.rgba).all()
+    assert (faces == full.face).all()
+
+
+def test_full_size_properties_1m_triangles(pkg, scene_dir):
+    """BASELINE configs[2] at full size (999 698 triangles, 1920x1080): properties that do not need
+    the oracle -- determinism, band invariance, background exactly where nothing is hit, t > 1e-5,
+    face ids in range, shadowed pixels black."""
+    capi = pkg.capi
+    capi.init(0)
+    arrs = scene_arrays("hf707_point_1920x1080_s20", pkg, scene_dir)
+    scene = capi.Scene(*arrs)
+    W, H = 1920, 1080
+    cam = capi.default_camera(W, H)
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    p = capi.make_params(W, H, 0, 1, 0)
+    a = scene.render(cam, lights, p)
+    b = scene.render(cam, lights, p)
+    assert (a.rgba == b.rgba).all() and (a.face == b.face).all()  # deterministic despite atomics
+    miss = a.face < 0
+    assert (a.rgba[miss][:, :3] == 255).all()
+    assert (a.t[~miss] > 1e-5).all() and (a.face[~miss] < arrs[0].shape[0]).all()
+    assert a.stats["rays_primary"] == W * H and a.stats["rays_secondary"] == 0
+    assert a.stats["rays_shadow"] == int((~miss).sum())
+    # a 4-way band split reproduces the frame
+    st = np.zeros_like(a.rgba)
+    for r in range(4):
+        pr = capi.make_params(W, H, 0, 1, 0, band_rows=8, band_rank=r, band_world=4)
+        st[capi.local_row_map(pr)] = scene.render(cam, lights, pr, want_face=False, want_t=False, want_rgb=False).rgba
+    assert (st == a.rgba).all()
+
+
+def test_limits_and_errors(pkg, scene_dir):
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("cube_point_1000")
+    scene = capi.Scene(g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    cam = capi.default_camera(32, 32)
+    with pytest.raises(capi.RtError):  # > 25 lights (visibleLights[25])
+        scene.render(cam, capi.Lights(np.zeros((26, 3), np.float32)), capi.make_params(32, 32))
+    with pytest.raises(capi.RtError):  # 6 x 5 grid > 25 samples
+        scene.render(cam, capi.Lights(np.zeros((1, 3), np.float32)), capi.make_params(32, 32, 1, 0, -1, (6, 5)))
+    with pytest.raises(capi.RtError):  # random spherical light mode
+        scene.render(cam, capi.Lights(np.zeros((1, 3), np.float32)), capi.make_params(32, 32, 0, 0))
+    # empty scene and zero lights render (all background / all shadow)
+    empty = capi.Scene(np.zeros((0, 3, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3, 3), np.float32),
+                       np.zeros(0, np.int32), g["mats"])
+    fr = empty.render(cam, capi.Lights(np.array([[0, 0, 1]], np.float32)), capi.make_params(32, 32))
+    assert (fr.rgba[..., :3] == 255).all() and (fr.face == -1).all()
+    fr = scene.render(cam, capi.Lights(np.zeros((0, 3), np.float32)), capi.make_params(32, 32))
+    assert (fr.rgba[fr.face >= 0][:, :3] == 0).all()  # no light visible -> SHADOW (src/flyscene.cpp:699-710)

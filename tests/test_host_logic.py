@@ -153,3 +153,18 @@ def test_ppm_writer_matches_reference_text_layout(pkg, tmp_path):
     pkg.capi.write_ppm(p, rgba, binary=True)
     raw = open(p, "rb").read()
     assert raw.startswith(b"P6\n3 2\n255\n") and raw[-3:] == bytes([12, 216, 100])
+
+
+@pytest.mark.parametrize("case", ["cube_point_1000", "dodge_point_1000", "gallery_area_200x150", "hf32_point_256x144"])
+def test_reference_octree_shape(case, pkg):
+    """The product's re-derivation of the reference BoxTree (candidate filter) has the shape the
+    reference built: reachable leaves, inner nodes, face references, largest leaf."""
+    g = load_golden(case)
+    capi = pkg.capi
+    d = capi.RtSceneDesc()
+    verts = np.ascontiguousarray(g["verts"], np.float32)
+    d.n_faces = verts.shape[0]
+    d.verts = verts.ctypes.data
+    out = np.zeros(4, np.int64)
+    assert capi.lib().rt_ref_octree_stats(C.byref(d), 1000, out.ctypes.data) == 0
+    assert (out == g["octree_stats"]).all(), (out, g["octree_stats"])
