@@ -189,6 +189,21 @@ int rt_light_strikes(RtScene *scene, int64_t n, const float *hit_points, const R
 /* BoundingBox::boxIntersect (src/boundingBox.cpp:48-83) against the scene root box for n segments
  * origin -> dest; hit_out [n] uint8 */
 int rt_box_intersect(RtScene *scene, int64_t n, const float *origins, const float *dests, uint8_t *hit_out);
+/* BoundingBox::boxIntersect (src/boundingBox.cpp:48-83) for an arbitrary box (BoundingBox(min,max)) */
+int rt_box_intersect_box(const float mn[3], const float mx[3], int64_t n, const float *origins, const float *dests,
+                         uint8_t *hit_out);
+/* Flyscene::rayTriangleIntersection (src/flyscene.cpp:787-819) for n (ray, face id) pairs;
+ * t_out[i] = t or the reference's miss sentinel -72 */
+int rt_ray_triangle(RtScene *scene, int64_t n, const float *origins, const float *dirs, const int32_t *faces,
+                    float *t_out);
+/* BoxTree::intersect (src/boxTree.cpp:150-173): the candidate face ids the reference's octree offers
+ * for the query origin -> dest, ascending (the std::set order).  Returns the count (may exceed cap;
+ * only the first cap ids are written) or < 0. */
+int rt_octree_candidates(RtScene *scene, const float origin[3], const float dest[3], int32_t *ids, int32_t cap);
+/* Flyscene::phongShade (src/flyscene.cpp:822-859) for n (ray origin, hit point, face id) triples;
+ * shadow rays for every light sample are traced as lightStrikes does.  rgb_out [n][3] */
+int rt_phong_shade(RtScene *scene, int64_t n, const float *origins, const float *hit_points, const int32_t *faces,
+                   const RtLights *lights, const RtParams *params, float *rgb_out);
 /* Camera::screenToWorld (tucano/camera.hpp:155-173) for n pixel coordinates; out [n][3] */
 int rt_screen_to_world(const RtCamera *cam, int64_t n, const float *pixels_xy, float *out);
 /* Flyscene::createSpherePoint / arealight::getPointLights (src/flyscene.cpp:962-972,

@@ -96,6 +96,7 @@ def lib():
         L.or_light_strikes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.or_trace_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_phong_shade.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.or_quantize.restype = C.c_int
         L.or_quantize.argtypes = [C.c_float]
         L.or_render_pixels.argtypes = [C.c_void_p, C.POINTER(OrCamera), C.c_void_p, C.c_int, C.c_void_p,

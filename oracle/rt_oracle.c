@@ -557,6 +557,12 @@ static v3 phong_shade(const OrScene *s, v3 origin, v3 hit, int face, const float
   return final;
 }
 
+void or_phong_shade(const OrScene *s, const float origin[3], const float hit[3], int face, const float *lights,
+                    int n_lights, float rgb[3]) {
+  v3 c = phong_shade(s, ld3(origin), ld3(hit), face, lights, n_lights, NULL);
+  st3(rgb, c);
+}
+
 /* a11 Flyscene::fresnel, src/flyscene.cpp:890-910 */
 static float fresnel(v3 I, v3 N, float ior) {
   float cosi = dot(I, N);

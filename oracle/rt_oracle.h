@@ -91,6 +91,9 @@ float or_ray_triangle(const OrScene *s, const float o[3], const float d[3], int 
 int or_light_samples(const OrParams *p, const float light[3], float *out /*[25][3]*/);
 /* a8 -- lightStrikes, src/flyscene.cpp:912-954 */
 int or_light_strikes(const OrScene *s, const float hit[3], const float *lights, int n, uint8_t *visible);
+/* a9 -- phongShade, src/flyscene.cpp:822-859 */
+void or_phong_shade(const OrScene *s, const float origin[3], const float hit[3], int face, const float *lights,
+                    int n_lights, float rgb[3]);
 /* a3 -- traceRay, src/flyscene.cpp:651-771.  Also reports the first hit (face id or -1, t). */
 void or_trace_ray(const OrScene *s, const float o[3], const float d[3], int level, const float *lights,
                   int n_lights, float rgb[3], int32_t *face, float *t);

@@ -70,7 +70,8 @@ API_SYMBOLS = [
     "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_ref_octree_stats",
     "rt_scene_debug_bvh",
     "rt_render", "rt_render_device", "rt_local_rows", "rt_local_row_map", "rt_trace_rays",
-    "rt_light_strikes", "rt_box_intersect", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm",
+    "rt_light_strikes", "rt_box_intersect", "rt_box_intersect_box", "rt_ray_triangle", "rt_octree_candidates",
+    "rt_phong_shade", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm",
 ]
 
 _lib = None
@@ -112,6 +113,10 @@ def lib():
     L.rt_trace_rays.argtypes = [vp, i64, f32p, f32p, C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp]
     L.rt_light_strikes.argtypes = [vp, i64, f32p, C.POINTER(RtLights), vp]
     L.rt_box_intersect.argtypes = [vp, i64, f32p, f32p, vp]
+    L.rt_box_intersect_box.argtypes = [vp, vp, i64, f32p, f32p, vp]
+    L.rt_ray_triangle.argtypes = [vp, i64, f32p, f32p, vp, vp]
+    L.rt_octree_candidates.argtypes = [vp, vp, vp, vp, i32]
+    L.rt_phong_shade.argtypes = [vp, i64, f32p, f32p, vp, C.POINTER(RtLights), C.POINTER(RtParams), vp]
     L.rt_screen_to_world.argtypes = [C.POINTER(RtCamera), i64, f32p, vp]
     L.rt_light_samples.argtypes = [C.POINTER(RtParams), vp, vp]
     L.rt_write_ppm.argtypes = [C.c_char_p, vp, i32, i32, i32]
@@ -353,12 +358,46 @@ class Scene:
         _check(lib().rt_light_strikes(self.h, h.shape[0], _ptr(h), C.byref(lights.c), _ptr(out)))
         return out
 
+    def ray_triangle(self, origins, dirs, faces):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        f = np.ascontiguousarray(faces, np.int32)
+        out = np.zeros(o.shape[0], np.float32)
+        _check(lib().rt_ray_triangle(self.h, o.shape[0], _ptr(o), _ptr(d), _ptr(f), _ptr(out)))
+        return out
+
+    def octree_candidates(self, origin, dest):
+        o = np.ascontiguousarray(origin, np.float32)
+        d = np.ascontiguousarray(dest, np.float32)
+        ids = np.zeros(max(1, self.n_faces), np.int32)
+        n = _check(lib().rt_octree_candidates(self.h, _ptr(o), _ptr(d), _ptr(ids), ids.shape[0]))
+        return ids[:n].copy()
+
+    def phong_shade(self, origins, hits, faces, lights: Lights, params: RtParams):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        h = np.ascontiguousarray(hits, np.float32).reshape(-1, 3)
+        f = np.ascontiguousarray(faces, np.int32)
+        out = np.zeros((o.shape[0], 3), np.float32)
+        _check(lib().rt_phong_shade(self.h, o.shape[0], _ptr(o), _ptr(h), _ptr(f), C.byref(lights.c), C.byref(params),
+                                    _ptr(out)))
+        return out
+
     def box_intersect(self, origins, dests):
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
         d = np.ascontiguousarray(dests, np.float32).reshape(-1, 3)
         out = np.zeros(o.shape[0], np.uint8)
         _check(lib().rt_box_intersect(self.h, o.shape[0], _ptr(o), _ptr(d), _ptr(out)))
         return out
+
+
+def box_intersect_box(mn, mx, origins, dests):
+    mn = np.ascontiguousarray(mn, np.float32)
+    mx = np.ascontiguousarray(mx, np.float32)
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dests, np.float32).reshape(-1, 3)
+    out = np.zeros(o.shape[0], np.uint8)
+    _check(lib().rt_box_intersect_box(_ptr(mn), _ptr(mx), o.shape[0], _ptr(o), _ptr(d), _ptr(out)))
+    return out
 
 
 def screen_to_world(cam: RtCamera, pixels_xy):

@@ -844,6 +844,85 @@ extern "C" int rt_box_intersect(RtScene *sc, int64_t n, const float *origins, co
   return RT_OK;
 }
 
+extern "C" int rt_box_intersect_box(const float mn[3], const float mx[3], int64_t n, const float *origins,
+                                    const float *dests, uint8_t *hit_out) {
+  if (!mn || !mx || !origins || !dests || !hit_out) return fail(RT_ERR_INVALID, "null argument");
+  if (n <= 0) return RT_OK;
+  int rc = ensure_device();
+  if (rc) return rc;
+  DevBuf in, out;
+  if ((rc = in.reserve((size_t)n * 24)) || (rc = out.reserve((size_t)n))) { in.release(); out.release(); return rc; }
+  float *d_o = in.as<float>(), *d_d = d_o + (size_t)n * 3;
+  cudaMemcpy(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_d, dests, (size_t)n * 12, cudaMemcpyHostToDevice);
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, g_sm_count * 16));
+  k_box_intersect_box<<<blocks, 256>>>(make_float3(mn[0], mn[1], mn[2]), make_float3(mx[0], mx[1], mx[2]), n, d_o, d_d,
+                                       out.as<uint8_t>());
+  cudaError_t e = cudaMemcpy(hit_out, out.p, (size_t)n, cudaMemcpyDeviceToHost);
+  in.release(); out.release();
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "box_intersect_box: %s", cudaGetErrorString(e));
+  return RT_OK;
+}
+
+extern "C" int rt_ray_triangle(RtScene *sc, int64_t n, const float *origins, const float *dirs, const int32_t *faces,
+                               float *t_out) {
+  if (!sc || !origins || !dirs || !faces || !t_out) return fail(RT_ERR_INVALID, "null argument");
+  if (n <= 0) return RT_OK;
+  int rc = ensure_device();
+  if (rc) return rc;
+  if ((rc = sc->in_a.reserve((size_t)n * 28)) || (rc = sc->in_b.reserve((size_t)n * 4))) return rc;
+  float *d_o = sc->in_a.as<float>(), *d_d = d_o + (size_t)n * 3;
+  int32_t *d_f = (int32_t *)(d_d + (size_t)n * 3);
+  CUDA_TRY(cudaMemcpy(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_f, faces, (size_t)n * 4, cudaMemcpyHostToDevice));
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, g_sm_count * 16));
+  k_ray_triangle<<<blocks, 256>>>(sc->dev, n, d_o, d_d, d_f, sc->in_b.as<float>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(t_out, sc->in_b.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+extern "C" int rt_octree_candidates(RtScene *sc, const float origin[3], const float dest[3], int32_t *ids, int32_t cap) {
+  if (!sc || !origin || !dest || (!ids && cap > 0)) return fail(RT_ERR_INVALID, "null argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  const int T = sc->dev.n_faces;
+  if (T == 0) return 0;
+  if ((rc = sc->in_b.reserve((size_t)T))) return rc;
+  const int blocks = std::max(1, std::min((T + 255) / 256, g_sm_count * 16));
+  k_octree_candidates<<<blocks, 256>>>(sc->dev, make_float3(origin[0], origin[1], origin[2]),
+                                       make_float3(dest[0], dest[1], dest[2]), sc->in_b.as<uint8_t>());
+  CUDA_TRY(cudaGetLastError());
+  std::vector<uint8_t> flag((size_t)T);
+  CUDA_TRY(cudaMemcpy(flag.data(), sc->in_b.p, (size_t)T, cudaMemcpyDeviceToHost));
+  int count = 0;
+  for (int f = 0; f < T; ++f)
+    if (flag[f]) { if (count < cap) ids[count] = f; ++count; }
+  return count;
+}
+
+extern "C" int rt_phong_shade(RtScene *sc, int64_t n, const float *origins, const float *hit_points, const int32_t *faces,
+                              const RtLights *lights, const RtParams *p, float *rgb_out) {
+  if (!sc || !origins || !hit_points || !faces || !lights || !p || !rgb_out) return fail(RT_ERR_INVALID, "null argument");
+  if (n <= 0) return RT_OK;
+  int rc = ensure_device();
+  if (rc) return rc;
+  FrameParams fp;
+  if ((rc = fill_frame(fp, nullptr, lights, p))) return rc;
+  if ((rc = sc->in_a.reserve((size_t)n * 28)) || (rc = sc->in_b.reserve((size_t)n * 12))) return rc;
+  float *d_o = sc->in_a.as<float>(), *d_h = d_o + (size_t)n * 3;
+  int32_t *d_f = (int32_t *)(d_h + (size_t)n * 3);
+  CUDA_TRY(cudaMemcpy(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_h, hit_points, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_f, faces, (size_t)n * 4, cudaMemcpyHostToDevice));
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, g_sm_count * 16));
+  k_phong_shade<<<blocks, 128>>>(sc->dev, fp, n, d_o, d_h, d_f, sc->in_b.as<float>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(rgb_out, sc->in_b.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
 extern "C" int rt_screen_to_world(const RtCamera *cam, int64_t n, const float *pixels_xy, float *out) {
   if (!cam || !pixels_xy || !out) return fail(RT_ERR_INVALID, "null argument");
   if (n <= 0) return RT_OK;

@@ -327,6 +327,43 @@ __device__ __forceinline__ V3 blend(RecType ty, V3 P, float f, V3 child) {
   return c;
 }
 
+// surface data at a hit: face normal, un-normalised interpolated normal, material id
+// (getInterpolatedNormal, src/flyscene.cpp:864-888; for spheres the radial direction)
+__device__ __forceinline__ void surface_at(const DevScene &sc, int face, V3 hit, V3 &fn, V3 &nrm_in, int &mid) {
+  if (face < sc.n_faces) {
+    const float4 *sp = sc.shade + (size_t)face * 7;
+    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
+    const float4 s3 = __ldg(sp + 3), s4 = __ldg(sp + 4), s5 = __ldg(sp + 5), s6 = __ldg(sp + 6);
+    mid = __float_as_int(s0.w);
+    fn = mk(s6);
+    const V3 a = mk(s0), b = mk(s1), c = mk(s2);
+    const V3 v0 = sub(b, a), v1 = sub(c, a), v2 = sub(hit, a);
+    const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+    const float denom = d00 * d11 - d01 * d01;
+    const float bv = (d11 * d20 - d01 * d21) / denom;
+    const float bw = (d00 * d21 - d01 * d20) / denom;
+    const float bu = 1.0f - bv - bw;
+    nrm_in = add(add(mul(bu, mk(s3)), mul(bv, mk(s4))), mul(bw, mk(s5)));
+  } else {
+    const int si = face - sc.n_faces;
+    const float4 cr = __ldg(sc.spheres + si);
+    mid = __ldg(sc.sphere_mat + si);
+    nrm_in = sub(hit, mk(cr));
+    fn = normalized(nrm_in);
+  }
+}
+
+// one visible light sample of phongShade's inner loop (src/flyscene.cpp:844-854): diffuse + specular
+__device__ __forceinline__ V3 phong_sample(V3 Ikd, V3 Iks, float shininess, V3 hit, V3 spos, V3 normal, V3 eye) {
+  const V3 ldir = normalized(sub(spos, hit));
+  const float costheta = max_std(0.0f, dot(ldir, normal));
+  const V3 diffuse = mul(costheta, Ikd);
+  const V3 refl = normalized(sub(ldir, mul(2.f * dot(ldir, normal), normal)));
+  const float cosphi = max_std(0.0f, dot(eye, mul(-1.f, refl)));
+  const V3 specular = mul(pow_ref(cosphi, shininess), Iks);
+  return add(diffuse, specular);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: shade one bounce level.  One thread per ray that hit (hit_list slot); warps stay converged
 // around the queue append (ballot + popc, one atomic per warp).
@@ -362,28 +399,7 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
         // ---- surface data ----
         V3 fn, nrm_in;
         int mid;
-        if (face < sc.n_faces) {
-          const float4 *sp = sc.shade + (size_t)face * 7;
-          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);
-          const float4 s3 = __ldg(sp + 3), s4 = __ldg(sp + 4), s5 = __ldg(sp + 5), s6 = __ldg(sp + 6);
-          mid = __float_as_int(s0.w);
-          fn = mk(s6);
-          // getInterpolatedNormal, :864-888
-          const V3 a = mk(s0), b = mk(s1), c = mk(s2);
-          const V3 v0 = sub(b, a), v1 = sub(c, a), v2 = sub(hit, a);
-          const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
-          const float denom = d00 * d11 - d01 * d01;
-          const float bv = (d11 * d20 - d01 * d21) / denom;
-          const float bw = (d00 * d21 - d01 * d20) / denom;
-          const float bu = 1.0f - bv - bw;
-          nrm_in = add(add(mul(bu, mk(s3)), mul(bv, mk(s4))), mul(bw, mk(s5)));
-        } else {
-          const int si = face - sc.n_faces;
-          const float4 cr = __ldg(sc.spheres + si);
-          mid = __ldg(sc.sphere_mat + si);
-          nrm_in = sub(hit, mk(cr));
-          fn = normalized(nrm_in);
-        }
+        surface_at(sc, face, hit, fn, nrm_in, mid);
         const Material m = load_material(sc, mid);
         // ---- phongShade, :822-859 ----
         const V3 I = ld3(fp.light_color);
@@ -401,13 +417,7 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
             if (!v) continue;
             sum += 1.f;
             const V3 spos = fp.point_light ? lpos : area_sample(fp, lpos, s);
-            const V3 ldir = normalized(sub(spos, hit));
-            const float costheta = max_std(0.0f, dot(ldir, normal));
-            const V3 diffuse = mul(costheta, Ikd);
-            const V3 refl = normalized(sub(ldir, mul(2.f * dot(ldir, normal), normal)));
-            const float cosphi = max_std(0.0f, dot(eye, mul(-1.f, refl)));
-            const V3 specular = mul(pow_ref(cosphi, m.ns), Iks);
-            acc = add(acc, add(diffuse, specular));
+            acc = add(acc, phong_sample(Ikd, Iks, m.ns, hit, spos, normal, eye));
             samples_shaded++;
           }
           const float fa = sum / (float)ns, fb2 = 1.3f / (float)ns;
@@ -512,6 +522,95 @@ __global__ void __launch_bounds__(128) k_light_strikes(const DevScene sc, const 
       occ = traverse<true, false>(sc, src, sub(hit, src), hit, tri_enabled, bt, bi, st);
     }
     out[g] = occ ? 0 : 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched per-function entry points (one thread per query; not on the frame path)
+// ---------------------------------------------------------------------------------------------
+// BoundingBox::boxIntersect against an arbitrary box
+__global__ void k_box_intersect_box(const float3 mn, const float3 mx, const int64_t n, const float *o, const float *dst,
+                                    uint8_t *out) {
+  const float bmn[3] = {mn.x, mn.y, mn.z}, bmx[3] = {mx.x, mx.y, mx.z};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = ref_box_intersect(bmn, bmx, ld3(o + 3 * i), ld3(dst + 3 * i)) ? 1 : 0;
+}
+
+// Flyscene::rayTriangleIntersection (src/flyscene.cpp:787-819) for (ray, face) pairs; -72 = miss
+__global__ void k_ray_triangle(const DevScene sc, const int64_t n, const float *o, const float *d, const int32_t *face,
+                               float *t_out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = face[i];
+    float res = -72.f;
+    if (f >= 0 && f < sc.n_faces) {
+      const float4 *sp = sc.shade + (size_t)f * 7;
+      const V3 a = mk(__ldg(sp)), b = mk(__ldg(sp + 1)), c = mk(__ldg(sp + 2)), nrm = mk(__ldg(sp + 6));
+      const V3 ro = ld3(o + 3 * i), rd = ld3(d + 3 * i);
+      const float den = dot(rd, nrm);
+      if (den != 0.f) {
+        const float t = (dot(nrm, a) - dot(ro, nrm)) / den;
+        const V3 P = add(ro, mul(t, rd));
+        const V3 v0 = sub(c, a), v1 = sub(b, a), v2 = sub(P, a);
+        const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d02 = dot(v0, v2), d12 = dot(v1, v2);
+        const float inv = 1.f / (d00 * d11 - d01 * d01);
+        const float u = (d11 * d02 - d01 * d12) * inv, v = (d00 * d12 - d01 * d02) * inv;
+        if ((u >= 0.f) && (v >= 0.f) && (u + v < 1.f)) res = t;
+      }
+    }
+    t_out[i] = res;
+  }
+}
+
+// BoxTree::intersect (src/boxTree.cpp:150-173): flag[f] = 1 iff the reference octree offers face f
+// for the query (origin, dest).  One thread per face.
+__global__ void k_octree_candidates(const DevScene sc, const float3 o3, const float3 d3, uint8_t *flag) {
+  const V3 o = mk(o3.x, o3.y, o3.z), dest = mk(d3.x, d3.y, d3.z);
+  const bool root = ref_box_intersect(sc.root_min, sc.root_max, o, dest);
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < sc.n_faces; f += gridDim.x * blockDim.x)
+    flag[f] = (root && (sc.oct_box == nullptr || ref_candidate(sc, f, o, dest))) ? 1 : 0;
+}
+
+// Flyscene::phongShade (src/flyscene.cpp:822-859) for explicit (origin, hit point, face) triples with
+// the frame's light list; shadow rays for every sample are traced inline.
+__global__ void __launch_bounds__(128) k_phong_shade(const DevScene sc, const FrameParams fp, const int64_t n,
+                                                    const float *origins, const float *hits, const int32_t *faces,
+                                                    float *rgb_out) {
+  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  const int S = fp.point_light ? 1 : fp.usteps * fp.vsteps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int face = faces[i];
+    V3 P = mk(0.f, 0.f, 0.f);
+    if (face >= 0 && face < sc.n_faces + sc.n_spheres) {
+      const V3 o = ld3(origins + 3 * i), hit = ld3(hits + 3 * i);
+      V3 fn, nrm_in;
+      int mid;
+      surface_at(sc, face, hit, fn, nrm_in, mid);
+      const Material m = load_material(sc, mid);
+      const V3 I = ld3(fp.light_color);
+      const V3 normal = normalized(affine_point(sc.model, nrm_in));
+      const V3 eye = normalized(mul(-1.f, sub(hit, o)));
+      const V3 Ikd = cmul(I, m.kd), Iks = cmul(I, m.ks);
+      for (int l = 0; l < fp.n_lights; ++l) {
+        float sum = 0.f;
+        V3 acc = mk(0.f, 0.f, 0.f);
+        const V3 lpos = ld3(fp.lights + 3 * l);
+        for (int s = 0; s < S; ++s) {
+          const V3 spos = fp.point_light ? lpos : area_sample(fp, lpos, s);
+          const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, spos, hit);
+          bool occ = false;
+          if (tri_enabled || sc.n_spheres > 0) {
+            float bt = RT_NO_HIT_T; int bi = -1;
+            occ = traverse<true, false>(sc, spos, sub(hit, spos), hit, tri_enabled, bt, bi, st);
+          }
+          if (occ) continue;
+          sum += 1.f;
+          acc = add(acc, phong_sample(Ikd, Iks, m.ns, hit, spos, normal, eye));
+        }
+        const float fa = sum / (float)S, fb2 = 1.3f / (float)S;
+        P = add(P, mul(fb2, mul(fa, acc)));
+      }
+    }
+    rgb_out[3 * i] = P.x; rgb_out[3 * i + 1] = P.y; rgb_out[3 * i + 2] = P.z;
   }
 }
 

@@ -172,3 +172,87 @@ def test_limits_and_errors(pkg, scene_dir):
     assert (fr.rgba[..., :3] == 255).all() and (fr.face == -1).all()
     fr = scene.render(cam, capi.Lights(np.zeros((0, 3), np.float32)), capi.make_params(32, 32))
     assert (fr.rgba[fr.face >= 0][:, :3] == 0).all()  # no light visible -> SHADOW (src/flyscene.cpp:699-710)
+
+
+def test_ray_triangle_pairs(pkg, oracle_mod, scene_dir):
+    """Flyscene::rayTriangleIntersection for explicit (ray, face) pairs, incl. the -72 miss sentinel,
+    degenerate (sliver) faces of dodgeColorTest and den == 0."""
+    O = oracle_mod
+    g, cp, scene, orc = _setup("dodge_point_1000", pkg, O, scene_dir)
+    rng = np.random.default_rng(5)
+    n = 20000
+    T = g["verts"].shape[0]
+    faces = rng.integers(0, T, n).astype(np.int32)
+    faces[:200] = 11034  # collinear sliver named in SURVEY.md A.10
+    cent = g["verts"][faces].mean(1)
+    o = (cent + rng.normal(0, 0.5, (n, 3))).astype(np.float32)
+    d = ((cent + rng.normal(0, 0.01, (n, 3)) - o) * rng.uniform(0.5, 2, (n, 1))).astype(np.float32)
+    d[200:400] = 0  # den == 0
+    got = scene.ray_triangle(o, d, faces)
+    exp = np.array([O.lib().or_ray_triangle(orc.handle, o[k].ctypes.data, d[k].ctypes.data, int(faces[k])) for k in range(n)],
+                   np.float32)
+    assert (got.view(np.uint32) == exp.view(np.uint32)).all()
+    assert (got == -72).any() and (got != -72).any()
+
+
+def test_octree_candidates_match_reference_boxtree(pkg, oracle_mod, scene_dir):
+    """BoxTree::intersect: candidate face sets for a handful of queries, incl. a ray lying in an octree
+    split plane (zero direction component -> NaN slab tests in the reference)."""
+    O = oracle_mod
+    g, cp, scene, orc = _setup("dodge_point_1000", pkg, O, scene_dir)
+    T = g["verts"].shape[0]
+    rng = np.random.default_rng(9)
+    queries = [((0, 0, 2), (0.1, 0.05, 1)), ((0, 0, 2), (0, 0, 1)), ((0, 0, 2), (0.3, 0, 1)), ((-1, 1, 1), (0.2, -0.1, 0.0))]
+    for _ in range(6):
+        queries.append((tuple(rng.uniform(-1.5, 1.5, 3)), tuple(rng.uniform(-0.5, 0.5, 3))))
+    buf = np.zeros(T, np.int32)
+    for o, dest in queries:
+        o = np.array(o, np.float32); dest = np.array(dest, np.float32)
+        got = scene.octree_candidates(o, dest)
+        n = O.lib().or_octree_candidates(orc.handle, o.ctypes.data, dest.ctypes.data, buf.ctypes.data, T)
+        root_hit = O.lib().or_box_intersect(g["root_min"].ctypes.data, g["root_max"].ctypes.data, o.ctypes.data, dest.ctypes.data)
+        exp = buf[:n] if root_hit else buf[:0]
+        assert (got == exp).all(), (o, dest, len(got), n)
+
+
+def test_phong_shade_batch(pkg, oracle_mod, scene_dir):
+    """Flyscene::phongShade for explicit (origin, hit, face) triples, area-light mode with two lights."""
+    O = oracle_mod
+    g, cp, scene, orc = _setup("gallery_area_200x150", pkg, O, scene_dir)
+    lights_np = np.ascontiguousarray(g["lights"], np.float32)
+    # take real hit points from a render so that the triples are meaningful
+    capi = pkg.capi
+    cam = capi.make_camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    fr = scene.render(cam, capi.Lights(lights_np, g["light_color"]), capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], 0, cp["grid"]))
+    ys, xs = np.nonzero(fr.face >= 0)
+    sel = np.random.default_rng(2).choice(len(xs), 3000, replace=False)
+    ys, xs = ys[sel], xs[sel]
+    pix = np.stack([xs, ys], 1).astype(np.float32)
+    screen = capi.screen_to_world(cam, pix)
+    o = np.tile(np.asarray(g["eye"], np.float32), (len(xs), 1))
+    d = (screen - o).astype(np.float32)
+    hit = (o + fr.t[ys, xs][:, None].astype(np.float32) * d).astype(np.float32)
+    faces = fr.face[ys, xs].astype(np.int32)
+    got = scene.phong_shade(o, hit, faces, capi.Lights(lights_np, g["light_color"]),
+                            capi.make_params(8, 8, cp["area"], cp["point"], 0, cp["grid"]))
+    exp = np.zeros_like(got)
+    for k in range(len(xs)):
+        O.lib().or_phong_shade(orc.handle, o[k].ctypes.data, hit[k].ctypes.data, int(faces[k]), lights_np.ctypes.data,
+                               lights_np.shape[0], exp[k].ctypes.data)
+    assert np.allclose(got, exp, rtol=2e-6, atol=1e-7)
+    print(f"phong batch: bit-identical {(got.view(np.uint32) == exp.view(np.uint32)).all(1).mean():.5f}")
+
+
+def test_box_intersect_arbitrary_box(pkg, oracle_mod):
+    O = oracle_mod
+    pkg.capi.init(0)
+    rng = np.random.default_rng(13)
+    mn = np.array([-0.3, -0.2, -0.5], np.float32); mx = np.array([0.4, 0.1, 0.0], np.float32)
+    n = 5000
+    o = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    dest = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    dest[:300, 1] = o[:300, 1]  # zero y direction
+    got = pkg.capi.box_intersect_box(mn, mx, o, dest)
+    exp = np.array([O.lib().or_box_intersect(mn.ctypes.data, mx.ctypes.data, o[i].ctypes.data, dest[i].ctypes.data)
+                    for i in range(n)], np.uint8)
+    assert (got == exp).all()
