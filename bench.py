@@ -248,16 +248,45 @@ def run_reference_arm(args, wl, rays_per_pixel):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def gather_bands(local, rows_per_rank, width, rank, world, dist, torch):
-    """Gather interleaved row bands to rank 0 (NCCL) and scatter them into the final frame.
-    local: [max_rows, W, 4] uint8 device tensor (padded to the largest per-rank row count)."""
-    if world == 1:
-        return local
-    parts = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
-    dist.gather(local, parts, dst=0)
-    if rank != 0:
-        return None
-    return parts
+class BandGather:
+    """Interleaved row bands -> rank 0.  Ranks own different row counts (the last band may be partial),
+    so every rank sends a buffer padded to the largest count; rank 0 scatters the valid rows of each
+    part into the frame with one index_copy per rank.  The collective is dist.gather (NCCL on GPUs,
+    gloo in the CPU test)."""
+
+    def __init__(self, rows, width, height, rank, world, dist, torch, dev):
+        self.rank, self.world, self.dist, self.torch = rank, world, dist, torch
+        self.n_local = len(rows)
+        n = torch.tensor([self.n_local], dtype=torch.int64, device=dev)
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, n)
+        self.counts = [int(c.item()) for c in counts]
+        self.max_rows = max(self.counts)
+        padded = torch.full((self.max_rows,), -1, dtype=torch.int64, device=dev)
+        padded[: self.n_local] = torch.as_tensor(np.asarray(rows), dtype=torch.int64, device=dev)
+        maps = [torch.zeros(self.max_rows, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(maps, padded)
+        self.maps = [m[: self.counts[r]] for r, m in enumerate(maps)]
+        self.frame = torch.zeros((height, width, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
+        self.parts = [torch.empty((self.max_rows, width, 4), dtype=torch.uint8, device=dev) for _ in range(world)] \
+            if rank == 0 else None
+
+    def __call__(self, local_padded):
+        """local_padded: [max_rows, W, 4] uint8 (rows beyond n_local are ignored)."""
+        self.dist.gather(local_padded, self.parts, dst=0)
+        if self.rank != 0:
+            return None
+        for r in range(self.world):
+            self.frame.index_copy_(0, self.maps[r], self.parts[r][: self.counts[r]])
+        return self.frame
+
+
+def gather_frame(local, rows, width, height, rank, world, dist, torch, dev):
+    """One-shot helper (tests): gather `local` [n_local, W, 4] to the full frame on rank 0."""
+    g = BandGather(rows, width, height, rank, world, dist, torch, dev)
+    padded = torch.zeros((g.max_rows, width, 4), dtype=torch.uint8, device=dev)
+    padded[: len(rows)] = local
+    return g(padded)
 
 
 def main():
@@ -316,30 +345,16 @@ def main():
     lights = capi.Lights(np.array([[-1.0, 1.0, 1.0]], np.float32))  # src/flyscene.cpp:72
     params = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], BAND_ROWS, rank, world)
     rows = capi.lib().rt_local_rows(C.byref(params))
-    row_map = torch.from_numpy(capi.local_row_map(params).astype(np.int64)).to(dev)
-    max_rows = rows
-    if world > 1:
-        t = torch.tensor([rows], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        max_rows = int(t.item())
-        all_maps = [torch.zeros(max_rows, dtype=torch.int64, device=dev) for _ in range(world)]
-        padded = torch.full((max_rows,), -1, dtype=torch.int64, device=dev)
-        padded[:rows] = row_map
-        dist.all_gather(all_maps, padded)
+    gather = BandGather(capi.local_row_map(params), W, H, rank, world, dist, torch, dev) if world > 1 else None
+    max_rows = gather.max_rows if gather else rows
     local = torch.zeros((max_rows, W, 4), dtype=torch.uint8, device=dev)
-    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    valid_maps = [m[m >= 0] for m in all_maps] if world > 1 else None
-
     def step():
         scene.render_device(cam, lights, params, local.data_ptr(), stream=stream)
-        if world > 1:
-            parts = gather_bands(local, rows, W, rank, world, dist, torch)
-            if rank == 0:
-                for r in range(world):
-                    frame.index_copy_(0, valid_maps[r], parts[r][: valid_maps[r].numel()])
+        if gather is not None:
+            gather(local)
 
     # ---- one untimed stats frame: ray census, per-kernel times, traversal counters ----
     capi.set_option("stats", 1)
@@ -412,9 +427,9 @@ def main():
         for _ in range(k2):
             scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False,
                          out_rgba=host_np)
-            if world > 1:
-                # bands travel to rank 0 over NCCL from the device copy, then rank 0 reads the frame back
-                gather_bands(local, rows, W, rank, world, dist, torch)
+            if gather is not None:
+                # bands travel to rank 0 over NCCL from the device copy
+                gather(local)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
