@@ -356,6 +356,35 @@ def main():
         if gather is not None:
             gather(local)
 
+    # Fused alternative for N > 1: every rank's kernels store their pixels straight into rank 0's
+    # framebuffer through an NVLink peer mapping (CUDA IPC); a 4-byte all-reduce on the stream is the
+    # only collective left (completion signal).  The NCCL gather above is kept as the baseline.
+    shared = None
+    step_peer = None
+    if world > 1:
+        try:
+            hbuf = torch.zeros(64, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                shared = capi.SharedFrame(W, H)
+                hbuf.copy_(torch.frombuffer(bytearray(shared.handle), dtype=torch.uint8))
+            dist.broadcast(hbuf, src=0)
+            if rank != 0:
+                shared = capi.SharedFrame(W, H, bytes(hbuf.cpu().numpy().tobytes()))
+            params_peer = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], BAND_ROWS, rank, world)
+            params_peer.out_full_frame = 1
+            token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+            def step_peer():
+                scene.render_device(cam, lights, params_peer, shared.ptr.value, stream=stream)
+                dist.all_reduce(token)
+        except Exception as ex:  # peer mapping unavailable: keep the NCCL path only
+            print(f"[rank {rank}] peer-store path unavailable: {ex}", file=sys.stderr)
+            shared, step_peer = None, None
+        ok = torch.tensor([1 if step_peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            step_peer = None
+
     # ---- one untimed stats frame: ray census, per-kernel times, traversal counters ----
     capi.set_option("stats", 1)
     st = capi.RtStats()
@@ -369,35 +398,47 @@ def main():
         dist.all_reduce(rays_t)
     rays_total, n_primary, n_shadow, n_secondary = [float(x) for x in rays_t.tolist()]
 
-    # ---- warm-up ----
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-
     # ---- timed: exactly K steps, CUDA events on the launch stream, L2 flushed between steps ----
-    sampler = ClockSampler(local_rank)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        sampler_ = ClockSampler(local_rank)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler_.start()
+        w0 = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall_ = time.perf_counter() - w0
+        clocks_ = sampler_.stop()
+        ms_t = torch.tensor([float(sum(a.elapsed_time(b) for a, b in evs))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        return float(ms_t.item()), wall_, clocks_
+
     kernel_ms = {"trace": 0.0, "shadow": 0.0, "shade": 0.0}
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    wall0 = time.perf_counter()
-    for a, b in evs:
-        flush.zero_()
-        a.record()
-        step()
-        b.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    ms_local = float(sum(a.elapsed_time(b) for a, b in evs))
-    ms_t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_t.item())
+    ms_total, wall, clocks = timed(step)
+    nccl_line = None
+    if step_peer is not None:
+        ms_peer, wall_peer, clocks_peer = timed(step_peer)
+        nccl_line = {"value": rays_total * args.steps / (ms_total * 1e-3) / 1e6, "ms_per_step": ms_total / args.steps,
+                     "note": "baseline: bands gathered to rank 0 with torch.distributed.gather (NCCL) + scatter"}
+        # correctness of the fused path: rank 0's peer-assembled frame == the NCCL-gathered frame
+        match = None
+        torch.cuda.synchronize(); dist.barrier()
+        if rank == 0:
+            match = bool((torch.from_numpy(shared.to_host()).to(dev) == gather.frame).all().item())
+        ms_total, wall, clocks = ms_peer, wall_peer, clocks_peer
+        nccl_line["frames_match"] = match
     ms_per_step = ms_total / args.steps
     value = rays_total * args.steps / (ms_total * 1e-3) / 1e6
 
@@ -411,36 +452,51 @@ def main():
         kernel_ms["shadow"] += s2.ms_shadow / reps
         kernel_ms["shade"] += s2.ms_shade / reps
 
-    # ---- e2e: rt_render() with pinned host buffers, copies inside the timed region ----
-    e2e = None
-    if True:
-        k2 = args.e2e_steps or min(args.steps, 20)
+    # ---- e2e: the user-facing blocking call with pinned HOST buffers, copies inside the timed region ----
+    # N = 1: rt_render() (H2D of camera/lights/params, render, D2H of the packed frame).
+    # N > 1: every rank renders its bands (fused peer store, else NCCL gather) and rank 0 reads the
+    # assembled full frame back to pinned host memory.
+    k2 = args.e2e_steps or min(args.steps, 20)
+    h2d = C.sizeof(capi.RtCamera) + C.sizeof(capi.RtParams) + 12 * lights.c.n + 16
+    if world == 1:
         host = torch.zeros((rows, W, 4), dtype=torch.uint8).pin_memory()
         host_np = host.numpy()
-        for _ in range(2):
+
+        def e2e_step():
             scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False,
                          out_rgba=host_np)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(k2):
-            scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False,
-                         out_rgba=host_np)
-            if gather is not None:
-                # bands travel to rank 0 over NCCL from the device copy
-                gather(local)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        dt = time.perf_counter() - t0
-        dt_t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-        dt = float(dt_t.item())
-        h2d = C.sizeof(capi.RtCamera) + C.sizeof(capi.RtParams) + 12 * lights.c.n + 16
-        e2e = {"value": rays_total * k2 / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(rows * W * 4), "ms_per_step": 1e3 * dt / k2, "steps": k2}
+    else:
+        host = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+        host_np = host.numpy()
+        fn = step_peer if step_peer is not None else step
+
+        def e2e_step():
+            fn()
+            torch.cuda.synchronize()
+            if rank == 0:
+                if step_peer is not None:
+                    capi.lib().rt_device_copy_to_host(host_np.ctypes.data, shared.ptr, host_np.nbytes)
+                else:
+                    host.copy_(gather.frame)
+                    torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    dt_t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+    dt = float(dt_t.item())
+    e2e = {"value": rays_total * k2 / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d) * world,
+           "d2h_bytes_per_step": int(H * W * 4), "ms_per_step": 1e3 * dt / k2, "steps": k2}
 
     if rank != 0:
         if world > 1:
@@ -505,7 +561,10 @@ def main():
                    "spheres": int(0 if spheres is None else len(spheres)), "lights": 1,
                    "samples_per_light": 1 if wl["point"] else wl["grid"][0] * wl["grid"][1],
                    "max_depth": wl["max_depth"], "l2": "flushed between timed frames (512 MiB memset)",
-                   "parallelism": f"{world} x interleaved {BAND_ROWS}-row bands, NCCL gather to rank 0" if world > 1 else "1 GPU",
+                   "parallelism": (f"{world} x interleaved {BAND_ROWS}-row bands; " +
+                                   ("kernels store pixels into rank 0's framebuffer over NVLink peer memory (CUDA IPC), "
+                                    "4-byte NCCL all-reduce as completion signal" if nccl_line else "NCCL gather to rank 0"))
+                   if world > 1 else "1 GPU",
                    "bvh": info},
         "rays": {"per_frame": rays_total, "primary": n_primary, "shadow": n_shadow, "secondary": n_secondary,
                  "note": "gate and sample shadow rays are separate queries in area mode (as in the reference); "
@@ -513,7 +572,7 @@ def main():
         "mpix_per_s": W * H * args.steps / (ms_total * 1e-3) / 1e6,
         "work": {k: stats[k] for k in ("box_tests", "tri_tests", "box_tests_shadow", "tri_tests_shadow", "shade_samples")},
         "kernel_ms": kernel_ms, "gpu_launches": int(stats["kernel_launches"] * args.steps),
-        "clocks": clocks, "wall_s": wall, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "wall_s": wall, "nccl_gather_baseline": nccl_line, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

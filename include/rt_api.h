@@ -95,6 +95,10 @@ typedef struct {
    * band = band_rows full-width rows; output buffers then hold only the local rows, packed in
    * ascending row order.  band_world <= 1 renders the whole image. */
   int32_t band_rows, band_rank, band_world;
+  /* rt_render_device only: 1 = d_rgba is the FULL height x width frame and every rendered row is
+   * stored at its global position (used to write bands straight into rank 0's framebuffer over an
+   * NVLink peer mapping, see rt_shared_frame_*); 0 = d_rgba holds the local rows, packed. */
+  int32_t out_full_frame;
 } RtParams;
 
 typedef struct {
@@ -176,6 +180,13 @@ int rt_render_device(RtScene *scene, const RtCamera *cam, const RtLights *lights
 int rt_local_rows(const RtParams *params);
 /* global row index of each local row (ascending); rows_out has rt_local_rows entries */
 int rt_local_row_map(const RtParams *params, int32_t *rows_out);
+
+/* ---- multi-GPU: a framebuffer shared between the per-GPU processes (CUDA IPC over NVLink) ------------
+ * Replaces the reference's shared pixel_data array written by all pool workers (src/flyscene.cpp:620). */
+int rt_shared_frame_create(size_t bytes, void **d_ptr, unsigned char handle[64]); /* owner (rank 0) */
+int rt_shared_frame_open(const unsigned char handle[64], void **d_ptr);           /* other ranks */
+int rt_shared_frame_close(void *d_ptr, int owner);
+int rt_device_copy_to_host(void *host, const void *d_ptr, size_t bytes);
 
 /* ---- per-function entry points (batched) --------------------------------------------------- */
 /* Flyscene::traceRay (src/flyscene.cpp:651-771) for n arbitrary rays: rgb_out [n][3] float,

@@ -49,7 +49,8 @@ class RtParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("area_light", C.c_int32),
                 ("point_light", C.c_int32), ("max_depth", C.c_int32), ("usteps", C.c_int32),
                 ("vsteps", C.c_int32), ("area_len_x", C.c_float), ("area_len_y", C.c_float),
-                ("band_rows", C.c_int32), ("band_rank", C.c_int32), ("band_world", C.c_int32)]
+                ("band_rows", C.c_int32), ("band_rank", C.c_int32), ("band_world", C.c_int32),
+                ("out_full_frame", C.c_int32)]
 
 
 class RtStats(C.Structure):
@@ -69,7 +70,8 @@ API_SYMBOLS = [
     "rt_default_params", "rt_mesh_load_obj", "rt_mesh_desc", "rt_mesh_info", "rt_mesh_destroy",
     "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_ref_octree_stats",
     "rt_scene_debug_bvh",
-    "rt_render", "rt_render_device", "rt_local_rows", "rt_local_row_map", "rt_trace_rays",
+    "rt_render", "rt_render_device", "rt_local_rows", "rt_local_row_map", "rt_shared_frame_create",
+    "rt_shared_frame_open", "rt_shared_frame_close", "rt_device_copy_to_host", "rt_trace_rays",
     "rt_light_strikes", "rt_box_intersect", "rt_box_intersect_box", "rt_ray_triangle", "rt_octree_candidates",
     "rt_phong_shade", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm",
 ]
@@ -108,6 +110,10 @@ def lib():
     L.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp, vp, vp]
     L.rt_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp,
                                    vp, vp, vp]
+    L.rt_shared_frame_create.argtypes = [C.c_size_t, C.POINTER(vp), vp]
+    L.rt_shared_frame_open.argtypes = [vp, C.POINTER(vp)]
+    L.rt_shared_frame_close.argtypes = [vp, C.c_int]
+    L.rt_device_copy_to_host.argtypes = [vp, vp, C.c_size_t]
     L.rt_local_rows.argtypes = [C.POINTER(RtParams)]
     L.rt_local_row_map.argtypes = [C.POINTER(RtParams), vp]
     L.rt_trace_rays.argtypes = [vp, i64, f32p, f32p, C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp]
@@ -412,6 +418,33 @@ def light_samples(params: RtParams, light):
     out = np.zeros((25, 3), np.float32)
     n = _check(lib().rt_light_samples(C.byref(params), _ptr(l), _ptr(out)))
     return out[:n].copy()
+
+
+class SharedFrame:
+    """A full-frame RGBA buffer on rank 0's GPU that the other ranks map through CUDA IPC (NVLink)."""
+
+    def __init__(self, width, height, handle: bytes | None = None):
+        self.w, self.h = width, height
+        self.ptr = C.c_void_p()
+        self.owner = handle is None
+        if self.owner:
+            buf = (C.c_ubyte * 64)()
+            _check(lib().rt_shared_frame_create(width * height * 4, C.byref(self.ptr), buf))
+            self.handle = bytes(buf)
+        else:
+            buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+            _check(lib().rt_shared_frame_open(buf, C.byref(self.ptr)))
+            self.handle = handle
+
+    def to_host(self):
+        out = np.zeros((self.h, self.w, 4), np.uint8)
+        _check(lib().rt_device_copy_to_host(_ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def close(self):
+        if self.ptr:
+            lib().rt_shared_frame_close(self.ptr, int(self.owner))
+            self.ptr = C.c_void_p()
 
 
 def local_row_map(params: RtParams):

@@ -550,6 +550,7 @@ int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, con
   fp.width = p->width; fp.height = p->height;
   fp.band_rows = std::max(1, p->band_rows); fp.band_rank = p->band_rank; fp.band_world = p->band_world;
   fp.local_rows = rt_local_rows(p);
+  fp.out_full_frame = p->out_full_frame ? 1 : 0;
   fp.n_lights = lights->n;
   for (int i = 0; i < lights->n * 3; ++i) fp.lights[i] = lights->pos[i];
   memcpy(fp.light_color, lights->color, 12);
@@ -696,7 +697,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
     LevelBufs lv = sc->levels[level].bufs();
     LevelBufs nx = sc->levels[level + 1].bufs();
     timer.begin(2);
-    k_fold<<<elem_blocks, 256, 0, st>>>(lv, nx, level, level == 0 ? n0 : -1, fc, level == 0 ? d_rgba : nullptr,
+    k_fold<<<elem_blocks, 256, 0, st>>>(fp, lv, nx, level, level == 0 ? n0 : -1, fc, level == 0 ? d_rgba : nullptr,
                                         level == 0 ? d_rgbf : nullptr);
     timer.end();
     ++launches;
@@ -760,6 +761,9 @@ extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *light
   if (face_out && (rc = sc->out_face.reserve(n * 4))) return rc;
   if (t_out && (rc = sc->out_t.reserve(n * 4))) return rc;
   if (rgb_f32_out && (rc = sc->out_rgbf.reserve(n * 12))) return rc;
+  RtParams local_p = *p;
+  local_p.out_full_frame = 0;  // host outputs always hold this call's rows only
+  p = &local_p;
   rc = rt_render_device(sc, cam, lights, p, sc->out_rgba.p, face_out ? sc->out_face.as<int32_t>() : nullptr,
                         t_out ? sc->out_t.as<float>() : nullptr, rgb_f32_out ? sc->out_rgbf.as<float>() : nullptr,
                         nullptr, stats);
@@ -769,6 +773,46 @@ extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *light
   if (t_out) CUDA_TRY(cudaMemcpyAsync(t_out, sc->out_t.p, n * 4, cudaMemcpyDeviceToHost, 0));
   if (rgb_f32_out) CUDA_TRY(cudaMemcpyAsync(rgb_f32_out, sc->out_rgbf.p, n * 12, cudaMemcpyDeviceToHost, 0));
   CUDA_TRY(cudaStreamSynchronize(0));
+  return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-process framebuffer sharing (one process per GPU): rank 0 allocates the frame, the other ranks
+// map it over NVLink peer access and their kernels store pixels straight into it
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_shared_frame_create(size_t bytes, void **d_ptr, unsigned char handle[64]) {
+  if (!d_ptr || !handle || bytes == 0) return fail(RT_ERR_INVALID, "bad argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaMalloc(d_ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+  if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return fail(RT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+  memcpy(handle, &h, 64);
+  return RT_OK;
+}
+
+extern "C" int rt_shared_frame_open(const unsigned char handle[64], void **d_ptr) {
+  if (!d_ptr || !handle) return fail(RT_ERR_INVALID, "bad argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RT_OK;
+}
+
+extern "C" int rt_shared_frame_close(void *d_ptr, int owner) {
+  if (!d_ptr) return RT_OK;
+  if (owner) CUDA_TRY(cudaFree(d_ptr));
+  else CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+  return RT_OK;
+}
+
+extern "C" int rt_device_copy_to_host(void *host, const void *d_ptr, size_t bytes) {
+  if (!host || !d_ptr) return fail(RT_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaMemcpy(host, d_ptr, bytes, cudaMemcpyDeviceToHost));
   return RT_OK;
 }
 

@@ -68,6 +68,15 @@ __device__ __forceinline__ int global_row(const FrameParams &fp, int local_row) 
   return (band * fp.band_world + fp.band_rank) * fp.band_rows + within;
 }
 
+// Framebuffer slot of local pixel i.  Normally the output holds only this rank's rows, packed; with
+// fp.out_full_frame the output is the whole H x W frame (possibly a peer GPU's memory mapped over
+// NVLink) and every row goes to its global position, which removes the separate tile gather.
+__device__ __forceinline__ size_t fb_index(const FrameParams &fp, int i) {
+  if (!fp.out_full_frame) return (size_t)i;
+  const int row = i / fp.width, col = i - row * fp.width;
+  return (size_t)global_row(fp, row) * fp.width + col;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: nearest hit.  Persistent CTAs; each warp pulls 32 work items at a time from a global cursor.
 // Primary rays: one item = one pixel of an 8x4 tile (coherent warps); the ray is generated
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const 
       lv.rec[i] = make_float4(1.f, 1.f, 1.f, 1.f);
       lv.type[i] = (uint8_t)REC_TERMINAL;
       if (level == 0) {
-        if (fb) fb[i] = make_uchar4(255, 255, 255, 255);
+        if (fb) fb[fb_index(fp, i)] = make_uchar4(255, 255, 255, 255);
         if (rgb_f32) { rgb_f32[3 * (size_t)i] = 1.f; rgb_f32[3 * (size_t)i + 1] = 1.f; rgb_f32[3 * (size_t)i + 2] = 1.f; }
       }
     }
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
     lv.child[i] = spawn ? slot : -1;
     lv.type[i] = (uint8_t)ty;
     if (level == 0 && ty == REC_TERMINAL) {
-      if (fb) fb[i] = pack_pixel(colour);
+      if (fb) fb[fb_index(fp, i)] = pack_pixel(colour);
       if (rgb_f32) { rgb_f32[3 * (size_t)i] = colour.x; rgb_f32[3 * (size_t)i + 1] = colour.y; rgb_f32[3 * (size_t)i + 2] = colour.z; }
     }
   }
@@ -473,8 +482,8 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
 // ---------------------------------------------------------------------------------------------
 // K3b: fold level k from level k+1 (deepest first); level 0 writes the framebuffer.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fold(const LevelBufs lv, const LevelBufs nx, const int level, const int n0,
-                                             const FrameCounts *fc, uchar4 *fb, float *rgb_f32) {
+__global__ void __launch_bounds__(256) k_fold(const FrameParams fp, const LevelBufs lv, const LevelBufs nx, const int level,
+                                             const int n0, const FrameCounts *fc, uchar4 *fb, float *rgb_f32) {
   const int n = n0 >= 0 ? n0 : fc->n_rays[level];
   if (fc->n_rays[level + 1] == 0) return;  // nothing was spawned below this level
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(256) k_fold(const LevelBufs lv, const LevelBuf
     const V3 col = blend(ty, mk(r), r.w, mk(c));
     lv.rec[i] = make_float4(col.x, col.y, col.z, 1.f);
     if (level == 0) {
-      if (fb) fb[i] = pack_pixel(col);
+      if (fb) fb[fb_index(fp, i)] = pack_pixel(col);
       if (rgb_f32) { rgb_f32[3 * (size_t)i] = col.x; rgb_f32[3 * (size_t)i + 1] = col.y; rgb_f32[3 * (size_t)i + 2] = col.z; }
     }
   }
