@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 render path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5] [--impl ours|reference]
 
 Metric (BASELINE.json): Mrays/s and ms/frame at 1080p.  One "step" = one frame of the workload:
   c2 (default, the configuration the metric is quoted on): the bundled cube scene at 1920x1080 with
@@ -55,6 +55,8 @@ WORKLOADS = {
     "c4": dict(desc="synthetic 100352 triangles + 1000 spheres 3840x2160, AreaLight 4x4, depth 5 (BASELINE configs[3])",
                scene=("gen", "write_heightfield", (224,)), spheres=1000, w=3840, h=2160, area=1, point=0, max_depth=5,
                grid=(4, 4)),
+    "c5": dict(desc="synthetic height field 999698 triangles 7680x4320 (8K), point light, primary+shadow (BASELINE configs[4])",
+               scene=("gen", "write_heightfield", (707,)), w=7680, h=4320, area=0, point=1, max_depth=0, grid=(5, 5)),
 }
 
 
@@ -217,7 +219,7 @@ def run_reference_arm(args, wl, rays_per_pixel):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    stride = {"c1": 3, "c2": 4, "c3": 24, "c4": 48}[args.workload]
+    stride = {"c1": 3, "c2": 4, "c3": 24, "c4": 48, "c5": 96}[args.workload]
     try:
         rays_sample, pix_sample = census_rays(wl, stride)
         rays_per_pixel = rays_sample / max(1, pix_sample)
@@ -543,7 +545,7 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            stride = {"c1": 2, "c2": 3, "c3": 20, "c4": 40}[args.workload]
+            stride = {"c1": 2, "c2": 3, "c3": 20, "c4": 40, "c5": 80}[args.workload]
             s, pix, kind, thr = reference_sample(wl, stride)
             rpp = rays_total / (W * H)
             cpu_baseline = {"value": pix * rpp / s / 1e6, "unit": "Mrays/s", "cores": thr, "kind": kind,
@@ -570,7 +572,8 @@ def main():
                  "note": "gate and sample shadow rays are separate queries in area mode (as in the reference); "
                          "in point mode the identical gate/sample ray is traced and counted once"},
         "mpix_per_s": W * H * args.steps / (ms_total * 1e-3) / 1e6,
-        "work": {k: stats[k] for k in ("box_tests", "tri_tests", "box_tests_shadow", "tri_tests_shadow", "shade_samples")},
+        "work": {k: stats[k] for k in ("box_tests", "tri_tests", "box_tests_shadow", "tri_tests_shadow", "shade_samples",
+                                         "filter_checks", "filter_slow", "filter_rejects")},
         "kernel_ms": kernel_ms, "gpu_launches": int(stats["kernel_launches"] * args.steps),
         "clocks": clocks, "wall_s": wall, "nccl_gather_baseline": nccl_line, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

@@ -116,6 +116,8 @@ typedef struct {
    * ray-AABB and ray-triangle tests of the nearest-hit kernels (K1) and of the shadow kernels (K2) */
   int64_t box_tests, tri_tests, shade_samples;
   int64_t box_tests_shadow, tri_tests_shadow;
+  /* reference-candidate filter: winners checked, checks that needed the exact octree walk, rejections */
+  int64_t filter_checks, filter_slow, filter_rejects;
 } RtStats;
 
 typedef struct RtScene RtScene;   /* device-resident BVH + triangle soup + shading tables */
@@ -132,7 +134,9 @@ int rt_device_name(char *buf, size_t n);
 /* runtime knobs: "stats" (0/1 traversal counters), "leaf_size", "persistent_ctas_per_sm",
  * "reference_candidates" (default 1: scenes created afterwards filter BVH hits through the
  * reference's octree candidate sets so that the image matches the reference bit for bit; 0: plain
- * BVH = exact nearest hit over all faces) */
+ * BVH = exact nearest hit over all faces), "refill_below" (dynamic ray fetch: persistent warps hand new
+ * rays to their idle lanes once fewer than this many lanes are still traversing; 0 = only when all
+ * 32 are done) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);
 

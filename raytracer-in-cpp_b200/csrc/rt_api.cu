@@ -37,6 +37,7 @@ int g_opt_stats = 0;
 int g_opt_leaf = 4;
 int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
 int g_opt_ref_candidates = 1;
+int g_opt_refill_below = 0;  // dynamic fetch: refill a warp when fewer lanes than this still traverse (0 = when all are done)
 
 int fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -177,6 +178,7 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "leaf_size")) g_opt_leaf = std::max(1, std::min(16, value));
   else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
   else if (!strcmp(key, "reference_candidates")) g_opt_ref_candidates = value ? 1 : 0;
+  else if (!strcmp(key, "refill_below")) g_opt_refill_below = std::max(0, std::min(32, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
 }
@@ -336,21 +338,31 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     use_filter = !oct.root_is_leaf;  // a single-leaf octree offers every face whenever the root box is hit
     if (use_filter) {
       // Degenerate (sliver) faces: the reference's barycentric test is cancellation noise for them and
-      // reports hits far outside the triangle wherever the octree offers the face.
-      // Give such faces the union of their octree leaf boxes as BVH bounds so those phantom hits are
-      // found too; the candidate filter then decides exactly as the reference does.
+      // reports hits outside the triangle wherever the octree offers the face.  The
+      // error of u,v is ~ eps_float * (|w|/|e|) / sin^2(theta) (theta = angle between the edges):
+      //  * sin^2 <= 1e-7 (or a non-finite 1/det): phantom hits can lie anywhere in the face's octree
+      //    leaves -> give the face the union of its leaf boxes as BVH bounds;
+      //  * otherwise the hit point can leave the triangle by at most ~1e-6 * |e| / sin^2 -> pad the
+      //    face's box by that much (only matters below sin^2 ~ 1e-2).
+      // The candidate filter then decides exactly as the reference does.
       for (int i = 0; i < T; ++i) {
         const float *v = desc->verts + (size_t)i * 9;
         const float e0[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]}, e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]};
         const float d00 = hdot(e0, e0), d01 = hdot(e0, e1), d11 = hdot(e1, e1);
         const float det = d00 * d11 - d01 * d01;
-        if (det > 1e-3f * (d00 * d11)) continue;
-        for (int k = oct.face_off[i]; k < oct.face_off[i + 1]; ++k) {
-          const float *b = &oct.box[(size_t)oct.face_leaf[k] * 6];
-          for (int a = 0; a < 3; ++a) {
-            boxes[i].mn[a] = std::min(boxes[i].mn[a], b[a]);
-            boxes[i].mx[a] = std::max(boxes[i].mx[a], b[3 + a]);
+        const float sin2 = det / (d00 * d11);
+        if (sin2 > 1e-2f) continue;
+        if (!(sin2 > 1e-7f) || !std::isfinite(1.f / det)) {
+          for (int k = oct.face_off[i]; k < oct.face_off[i + 1]; ++k) {
+            const float *b = &oct.box[(size_t)oct.face_leaf[k] * 6];
+            for (int a = 0; a < 3; ++a) {
+              boxes[i].mn[a] = std::min(boxes[i].mn[a], b[a]);
+              boxes[i].mx[a] = std::max(boxes[i].mx[a], b[3 + a]);
+            }
           }
+        } else {
+          const float extra = 1e-6f * std::sqrt(std::max(d00, d11)) / sin2;
+          for (int a = 0; a < 3; ++a) { boxes[i].mn[a] -= extra; boxes[i].mx[a] += extra; }
         }
       }
     }
@@ -361,6 +373,7 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     diag = std::max(1.f, std::sqrt(dx * dx + dy * dy + dz * dz));
   }
   const float pad = 1e-5f * diag;  // see DESIGN.md "conservative culling"
+  sc->dev.oct_eps = 1e-5f * diag;
   const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   rt::BvhBuildResult bvh = rt::build_bvh(boxes, kind, g_opt_leaf, pad, threads);
   sc->n_leaves = bvh.n_leaves;
@@ -654,21 +667,21 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
     // ---- K1 ----
     timer.begin(0);
     if (level == 0 && !explicit_rays) {
-      if (trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf);
-      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf);
+      if (trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf, g_opt_refill_below);
+      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf, g_opt_refill_below);
     } else {
       uchar4 *fb0 = level == 0 ? d_rgba : nullptr;
       float *rgbf0 = level == 0 ? d_rgbf : nullptr;
       int32_t *face0 = level == 0 ? d_face : nullptr;
       float *t0 = level == 0 ? d_t : nullptr;
-      if (trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0);
-      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0);
+      if (trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0, g_opt_refill_below);
+      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0, g_opt_refill_below);
     }
     timer.end();
     // ---- K2 ----
     timer.begin(1);
-    if (trav_stats) k_shadow<true><<<grid_k2_s, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc);
-    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc);
+    if (trav_stats) k_shadow<true><<<grid_k2_s, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc, g_opt_refill_below);
+    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc, g_opt_refill_below);
     timer.end();
     // ---- K3 ----
     const bool may_spawn = level < depth_cap;
@@ -729,6 +742,9 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
     stats->shade_samples = (int64_t)h.ctr.shade_samples;
     stats->box_tests_shadow = (int64_t)h.ctr.box_tests_k2;
     stats->tri_tests_shadow = (int64_t)h.ctr.tri_tests_k2;
+    stats->filter_checks = (int64_t)h.ctr.filter_checks;
+    stats->filter_slow = (int64_t)h.ctr.filter_slow;
+    stats->filter_rejects = (int64_t)h.ctr.filter_rejects;
   }
   return RT_OK;
 }

@@ -50,6 +50,7 @@ struct Counters {
   unsigned long long shade_samples;  // K3
   unsigned long long box_tests_k2;   // K2 (shadow)
   unsigned long long tri_tests_k2;   // K2
+  unsigned long long filter_checks, filter_slow, filter_rejects;  // candidate filter (K1 + K2)
 };
 
 // Device-resident per-frame state, zeroed by one memset at frame start.  Ray and hit counts of every
@@ -84,84 +85,155 @@ __device__ __forceinline__ size_t fb_index(const FrameParams &fp, int i) {
 // level-0 pixel written); rays that hit are compacted into hit_list with one atomic per warp.
 // n0 >= 0: item count given by the host (level 0); n0 < 0: read fc->n_rays[level].
 // ---------------------------------------------------------------------------------------------
+// Lanes of a persistent warp are refilled with new rays as soon as fewer than this many are still
+// traversing (dynamic fetch); the traversal of the remaining lanes resumes where it stopped.
+// Work items a warp takes from the global cursor per atomic.  Small when the launch has little work
+// (so that every resident warp gets some), up to 96 when there is plenty (atomic off the critical path).
+__device__ __forceinline__ unsigned long long pool_batch(unsigned long long n_items) {
+  const unsigned long long warps_total = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  const unsigned long long per_warp = n_items / (warps_total * 8ull);
+  return per_warp >= 96ull ? 96ull : (per_warp >= 64ull ? 64ull : 32ull);
+}
+
 template <bool PRIMARY, bool STATS>
 __global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const FrameParams fp, const LevelBufs lv,
                                                       const int level, const int n0, FrameCounts *fc,
-                                                      int32_t *face_out, float *t_out, uchar4 *fb, float *rgb_f32) {
+                                                      int32_t *face_out, float *t_out, uchar4 *fb, float *rgb_f32,
+                                                      const int refill_below) {
   const int lane = threadIdx.x & 31;
-  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of work items (warp-uniform)
+  unsigned long long RT_POOL_BATCH = 32ull;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   const int tiles_x = PRIMARY ? (fp.width + 7) >> 3 : 1;
   const int n = n0 >= 0 ? n0 : fc->n_rays[level];
-  const int n_items = PRIMARY ? tiles_x * ((fp.local_rows + 3) >> 2) * 32 : n;
+  const long long n_items = PRIMARY ? (long long)tiles_x * ((fp.local_rows + 3) >> 2) * 32 : n;
   unsigned long long *cursor = &fc->work_k1[level];
+  RT_POOL_BATCH = pool_batch((unsigned long long)n_items);
+
+  Trav<false, STATS> tr;
+  int stack[RT_STACK_SIZE];
+  bool active = false;     // this lane holds a ray that is still being traversed
+  bool retire = false;     // this lane finished a ray in the previous round; results not yet written
+  bool exhausted = false;  // the work cursor ran past the end (warp-uniform)
+  int cur_i = 0;           // ray / local pixel index of the lane's ray
+  float fin_t = RT_NO_HIT_T;
+  int fin_id = -1;
+
   for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(cursor, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= (unsigned long long)n_items) break;
-    int i;
-    bool valid;
-    V3 o, d;
-    bool tri_enabled = true;
-    if constexpr (PRIMARY) {
-      const int tile = (int)(base >> 5);
-      const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-      const int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
-      valid = px < fp.width && py < fp.local_rows;
-      i = py * fp.width + px;
-      o = ld3(fp.eye);
-      d = mk(0.f, 0.f, 0.f);
-      if (valid) {
-        const V3 screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
-        // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
-        // (scenes with analytic spheres -- not a reference feature -- skip this pre-cull, like rt_oracle.c)
-        tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, o, screen) || sc.n_spheres > 0;
-        d = sub(screen, o);  // :619, not normalised
-      }
-    } else {
-      i = (int)base + lane;
-      valid = i < n;
-      if (valid) {
-        const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
-        o = mk(ro); d = mk(rd);
-      } else { o = mk(0, 0, 0); d = mk(0, 0, 0); }
-    }
-    float best_t = RT_NO_HIT_T;
-    int best_id = -1;
-    if (valid) {
-      // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
-      const V3 dest = add(o, d);
-      tri_enabled = tri_enabled && ref_box_intersect(sc.root_min, sc.root_max, o, dest);
-      if (tri_enabled || sc.n_spheres > 0) traverse<false, STATS>(sc, o, d, dest, tri_enabled, best_t, best_id, st);
-    }
-    const bool hit = valid && best_id >= 0;
-    const int slot = warp_append(&fc->n_hits[level], hit);
-    if (!valid) continue;
-    if (hit) {
-      if (PRIMARY) {
-        lv.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0));
-        lv.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
-      }
-      lv.hit_t[i] = best_t;
-      lv.hit_face[i] = best_id;
-      lv.hit_list[slot] = i;
-    } else {
-      // BACKGROUND, src/flyscene.cpp:658-665 / :684-691
-      lv.rec[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-      lv.type[i] = (uint8_t)REC_TERMINAL;
-      if (level == 0) {
-        if (fb) fb[fb_index(fp, i)] = make_uchar4(255, 255, 255, 255);
-        if (rgb_f32) { rgb_f32[3 * (size_t)i] = 1.f; rgb_f32[3 * (size_t)i + 1] = 1.f; rgb_f32[3 * (size_t)i + 2] = 1.f; }
+    // ---- retire finished rays (all 32 lanes converge here: one hit-list atomic per warp) ----
+    {
+      const bool hit = retire && fin_id >= 0;
+      const int slot = warp_append(&fc->n_hits[level], hit);
+      if (retire) {
+        const int i = cur_i;
+        if (hit) {
+          if (PRIMARY) {
+            lv.ray_o[i] = make_float4(tr.o.x, tr.o.y, tr.o.z, __int_as_float(0));
+            lv.ray_d[i] = make_float4(tr.d.x, tr.d.y, tr.d.z, 0.f);
+          }
+          lv.hit_t[i] = fin_t;
+          lv.hit_face[i] = fin_id;
+          lv.hit_list[slot] = i;
+        } else {
+          // BACKGROUND, src/flyscene.cpp:658-665 / :684-691
+          lv.rec[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+          lv.type[i] = (uint8_t)REC_TERMINAL;
+          if (level == 0) {
+            if (fb) fb[fb_index(fp, i)] = make_uchar4(255, 255, 255, 255);
+            if (rgb_f32) { rgb_f32[3 * (size_t)i] = 1.f; rgb_f32[3 * (size_t)i + 1] = 1.f; rgb_f32[3 * (size_t)i + 2] = 1.f; }
+          }
+        }
+        if (level == 0) {
+          if (face_out) face_out[i] = fin_id;
+          if (t_out) t_out[i] = fin_t;
+        }
+        retire = false;
       }
     }
-    if (level == 0) {
-      if (face_out) face_out[i] = best_id;
-      if (t_out) t_out[i] = best_t;
+    // ---- refill idle lanes ----
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (idle != 0u && !(exhausted && pool_next >= pool_end)) {
+      if (pool_next >= pool_end && !exhausted) {
+        // one global atomic per RT_POOL_BATCH items; lanes are then refilled from the warp-local pool
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, RT_POOL_BATCH);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        pool_next = base;
+        pool_end = base + RT_POOL_BATCH < (unsigned long long)n_items ? base + RT_POOL_BATCH : (unsigned long long)n_items;
+        if (base >= (unsigned long long)n_items) { exhausted = true; pool_end = pool_next; }
+      }
+      const unsigned long long my_item = pool_next + (unsigned long long)__popc(idle & lt_mask);
+      pool_next += (unsigned long long)__popc(idle);
+      if (!active) {
+        const long long item = (long long)my_item;
+        if (my_item < pool_end) {
+          int i;
+          bool valid;
+          V3 o, d;
+          bool tri_enabled = true;
+          if constexpr (PRIMARY) {
+            const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int px = tx * 8 + (in_tile & 7), py = ty * 4 + (in_tile >> 3);
+            valid = px < fp.width && py < fp.local_rows;
+            i = py * fp.width + px;
+            o = ld3(fp.eye);
+            d = mk(0.f, 0.f, 0.f);
+            if (valid) {
+              const V3 screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
+              // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
+              // (scenes with analytic spheres -- not a reference feature -- skip it, like rt_oracle.c)
+              tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, o, screen) || sc.n_spheres > 0;
+              d = sub(screen, o);  // :619, not normalised
+            }
+          } else {
+            i = (int)item;
+            valid = true;
+            const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
+            o = mk(ro); d = mk(rd);
+          }
+          if (valid) {
+            // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
+            const V3 dest = add(o, d);
+            tri_enabled = tri_enabled && ref_box_intersect(sc.root_min, sc.root_max, o, dest);
+            cur_i = i;
+            tr.init(o, d, dest, tri_enabled);
+            if (tri_enabled || sc.n_spheres > 0) {
+              active = true;
+            } else {
+              retire = true; fin_t = RT_NO_HIT_T; fin_id = -1;  // missed the root box: BACKGROUND
+            }
+          }
+        }
+      }
     }
+    const bool any_active = __any_sync(0xffffffffu, active);
+    const bool any_retire = __any_sync(0xffffffffu, retire);
+    if (!any_active) {
+      if (any_retire) continue;
+      if (exhausted && pool_next >= pool_end) break;
+      continue;
+    }
+    // ---- traverse (resumes where the lane stopped) ----
+    if (active) {
+      if (tr.run(sc, st, stack, (exhausted && pool_next >= pool_end) ? 1 : refill_below)) {
+        if (tr.finish(sc, st)) {
+          active = false;
+          retire = true;
+          fin_t = tr.best_t;
+          fin_id = tr.best_id;
+        }
+      }
+    }
+    __syncwarp();
   }
   if (STATS) {
     atomicAdd(&fc->ctr.box_tests, (unsigned long long)st.box_tests);
     atomicAdd(&fc->ctr.tri_tests, (unsigned long long)st.tri_tests);
+    atomicAdd(&fc->ctr.filter_checks, (unsigned long long)st.filter_checks);
+    atomicAdd(&fc->ctr.filter_slow, (unsigned long long)st.filter_slow);
+    atomicAdd(&fc->ctr.filter_rejects, (unsigned long long)st.filter_rejects);
   }
 }
 
@@ -206,56 +278,89 @@ __device__ __forceinline__ V3 area_sample(const FrameParams &fp, V3 c, int k) {
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FrameParams fp, const LevelBufs lv,
                                                const int level, const int J, const int Lmax, const int S,
-                                               FrameCounts *fc) {
+                                               FrameCounts *fc, const int refill_below) {
   const int lane = threadIdx.x & 31;
-  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of jobs (warp-uniform)
+  unsigned long long RT_POOL_BATCH = 32ull;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   unsigned traced = 0;
   const unsigned n_jobs = (unsigned)fc->n_hits[level] * (unsigned)J;
   unsigned long long *cursor = &fc->work_k2[level];
-  // grain: 4 x 32 jobs per cursor update when there is plenty of work (keeps the single-address
-  // atomic off the critical path), 32 when the job count is small (load balance over all warps)
-  const unsigned warps_total = gridDim.x * (blockDim.x >> 5);
-  const int reps = (n_jobs >= warps_total * 32u * 16u) ? 4 : 1;
+  RT_POOL_BATCH = pool_batch((unsigned long long)n_jobs);
+
+  Trav<true, STATS> tr;
+  int stack[RT_STACK_SIZE];
+  bool active = false, exhausted = false;
+  unsigned cur_g = 0;
+
   for (;;) {
-    unsigned long long base64 = 0;
-    if (lane == 0) base64 = atomicAdd(cursor, (unsigned long long)(32 * reps));
-    base64 = __shfl_sync(0xffffffffu, base64, 0);
-    if (base64 >= (unsigned long long)n_jobs) break;
-    const unsigned base = (unsigned)base64;
-#pragma unroll 1
-    for (int rep = 0; rep < reps; ++rep) {
-      const unsigned g = base + (unsigned)rep * 32u + (unsigned)lane;
-      if (g >= n_jobs) break;
-      const unsigned slot = g / (unsigned)J;
-      const int j = (int)(g - slot * (unsigned)J);
-      const int i = lv.hit_list[slot];
-      const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
-      const float2 rl2 = lv.ray_l[i];
-      const RayLights rl = ray_lights(fp, ro, rd, rl2);
-      int l;
-      V3 src;
-      if (j < Lmax) {
-        l = j;
-        if (l >= rl.n) { lv.vis[g] = 0; continue; }
-        src = light_pos(fp, rl, l);
-      } else {
-        const int s = j - Lmax;
-        l = s / S;
-        if (l >= rl.n) { lv.vis[g] = 0; continue; }
-        src = area_sample(fp, light_pos(fp, rl, l), s - l * S);
+    // ---- refill idle lanes with new shadow jobs ----
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (idle != 0u && !(exhausted && pool_next >= pool_end)) {
+      if (pool_next >= pool_end && !exhausted) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, RT_POOL_BATCH);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        pool_next = base;
+        pool_end = base + RT_POOL_BATCH < (unsigned long long)n_jobs ? base + RT_POOL_BATCH : (unsigned long long)n_jobs;
+        if (base >= (unsigned long long)n_jobs) { exhausted = true; pool_end = pool_next; }
       }
-      const V3 o = mk(ro), d = mk(rd);
-      const V3 hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
-      const V3 sd = sub(hit, src);                 // :920
-      const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);  // :924
-      bool occluded = false;
-      if (tri_enabled || sc.n_spheres > 0) {
-        float bt = RT_NO_HIT_T; int bi = -1;
-        occluded = traverse<true, STATS>(sc, src, sd, hit, tri_enabled, bt, bi, st);
+      const unsigned long long g64 = pool_next + (unsigned long long)__popc(idle & lt_mask);
+      pool_next += (unsigned long long)__popc(idle);
+      if (!active) {
+        if (g64 < pool_end) {
+          const unsigned g = (unsigned)g64;
+          const unsigned slot = g / (unsigned)J;
+          const int j = (int)(g - slot * (unsigned)J);
+          const int i = lv.hit_list[slot];
+          const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
+          const float2 rl2 = lv.ray_l[i];
+          const RayLights rl = ray_lights(fp, ro, rd, rl2);
+          int l;
+          V3 src = mk(0.f, 0.f, 0.f);
+          bool have = true;
+          if (j < Lmax) {
+            l = j;
+            if (l >= rl.n) have = false; else src = light_pos(fp, rl, l);
+          } else {
+            const int s = j - Lmax;
+            l = s / S;
+            if (l >= rl.n) have = false; else src = area_sample(fp, light_pos(fp, rl, l), s - l * S);
+          }
+          if (!have) {
+            lv.vis[g] = 0;
+          } else {
+            const V3 o = mk(ro), d = mk(rd);
+            const V3 hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
+            const V3 sd = sub(hit, src);                 // :920
+            const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);  // :924
+            traced++;
+            if (tri_enabled || sc.n_spheres > 0) {
+              tr.init(src, sd, hit, tri_enabled);
+              cur_g = g;
+              active = true;
+            } else {
+              lv.vis[g] = 1;  // nothing can occlude: t stays FLT_MAX >= 0.98 (:946)
+            }
+          }
+        }
       }
-      traced++;
-      lv.vis[g] = occluded ? 0 : 1;
     }
+    if (!__any_sync(0xffffffffu, active)) {
+      if (exhausted && pool_next >= pool_end) break;
+      continue;
+    }
+    // ---- traverse (resumes where the lane stopped) ----
+    if (active) {
+      if (tr.run(sc, st, stack, (exhausted && pool_next >= pool_end) ? 1 : refill_below)) {
+        if (tr.finish(sc, st)) {
+          lv.vis[cur_g] = tr.occluded ? 0 : 1;
+          active = false;
+        }
+      }
+    }
+    __syncwarp();
   }
   // census: one atomic per warp
   for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
@@ -263,6 +368,9 @@ __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FramePa
   if (STATS) {
     atomicAdd(&fc->ctr.box_tests_k2, (unsigned long long)st.box_tests);
     atomicAdd(&fc->ctr.tri_tests_k2, (unsigned long long)st.tri_tests);
+    atomicAdd(&fc->ctr.filter_checks, (unsigned long long)st.filter_checks);
+    atomicAdd(&fc->ctr.filter_slow, (unsigned long long)st.filter_slow);
+    atomicAdd(&fc->ctr.filter_rejects, (unsigned long long)st.filter_rejects);
   }
 }
 
@@ -519,7 +627,7 @@ __global__ void k_screen_to_world(const FrameParams fp, const int64_t n, const f
 __global__ void __launch_bounds__(128) k_light_strikes(const DevScene sc, const FrameParams fp, const int64_t n,
                                                       const float *hits, uint8_t *out) {
   const int L = fp.n_lights;
-  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n * L; g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = g / L;
     const int l = (int)(g - i * L);
@@ -584,7 +692,7 @@ __global__ void k_octree_candidates(const DevScene sc, const float3 o3, const fl
 __global__ void __launch_bounds__(128) k_phong_shade(const DevScene sc, const FrameParams fp, const int64_t n,
                                                     const float *origins, const float *hits, const int32_t *faces,
                                                     float *rgb_out) {
-  TravStats st; st.box_tests = 0; st.tri_tests = 0;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   const int S = fp.point_light ? 1 : fp.usteps * fp.vsteps;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int face = faces[i];

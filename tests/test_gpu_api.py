@@ -255,3 +255,38 @@ def test_box_intersect_arbitrary_box(pkg, oracle_mod):
     exp = np.array([O.lib().or_box_intersect(mn.ctypes.data, mx.ctypes.data, o[i].ctypes.data, dest[i].ctypes.data)
                     for i in range(n)], np.uint8)
     assert (got == exp).all()
+
+
+@pytest.mark.parametrize("area,point,depth", [(0, 1, 2), (1, 0, 3)])
+def test_analytic_spheres_match_the_port(area, point, depth, pkg, oracle_mod, scene_dir):
+    """BASELINE configs[3] adds analytic spheres, which the reference does not have (parity unpinned):
+    the CUDA path is checked against the definition in oracle/rt_oracle.c (ray_sphere) -- mixed
+    triangle + sphere scene, diffuse and mirror spheres, shadows cast by and onto spheres."""
+    O = oracle_mod
+    capi = pkg.capi
+    capi.init(0)
+    arrs = list(scene_arrays("hf32_point_256x144", pkg, scene_dir))
+    base = arrs[4].shape[0]
+    arrs[4] = np.concatenate([arrs[4], np.array([[0.8, 0.3, 0.2, 1, 1, 1, 30, 0, 2], [0.9, 0.9, 0.9, 1, 1, 1, 60, 0, 4],
+                                                 [0.2, 0.9, 0.9, 1, 1, 1, 20, 0, 9]], np.float32)], 0)
+    spheres = pkg.scenes.sphere_cloud(60, seed=4321)
+    spheres[:, 3] *= 3.0            # visible at this resolution
+    spheres[:, 2] = np.abs(spheres[:, 2]) * 0.6 + 0.15   # in front of the height field
+    sphere_mat = (base + (np.arange(len(spheres)) % 3)).astype(np.int32)
+    scene = capi.Scene(*arrs, None, spheres, sphere_mat)
+    W, H = 320, 200
+    lights_np = np.array([[-1, 1, 1.5], [0.8, 0.6, 2.0]], np.float32)
+    fr = scene.render(capi.default_camera(W, H), capi.Lights(lights_np), capi.make_params(W, H, area, point, depth, (3, 3)))
+    orc = O.Oracle(O.BakedScene(*arrs, spheres=spheres, sphere_mat=sphere_mat), area=area, point=point, max_depth=depth,
+                   grid=(3, 3))
+    cam = O.Oracle.camera((0, 0, 2), np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2]], np.float32), (0, 0, W, H), 60.0,
+                          np.float32(W) / np.float32(H))
+    pxy, rgb, face, t, rgb8 = orc.render(cam, lights_np, W, H, stride=1, threads=8)
+    px, py = pxy[:, 0], pxy[:, 1]
+    T = arrs[0].shape[0]
+    assert (face >= T).sum() > 500, "spheres should be visible"
+    assert (fr.face[py, px] == face).all()
+    assert (fr.t[py, px].view(np.uint32) == t.view(np.uint32)).all()
+    exp = np.clip(O.quantize(rgb), 0, 255)
+    err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - exp).max(-1)
+    assert err.max() <= 1 and (err == 0).mean() > 0.999, f"max err {err.max()}, exact {(err == 0).mean()}"
