@@ -391,10 +391,22 @@ __device__ __forceinline__ Material load_material(const DevScene &sc, int mid) {
 
 // powf as the reference's libm computes it: glibc's powf is correctly rounded in all but
 // astronomically rare cases; CUDA's float powf is not (up to 4 ulp), so evaluate in double and
-// round once.  pow(0, y>0) = 0 and pow(1, y) = 1 short-cut the common cases.
+// round once.  Integer exponents (the usual MTL "Ns 10" / "Ns 50") use binary powering: <= 2*log2(n)
+// double multiplications, relative error <= ~n * 1.1e-16, i.e. closer to the true value than a
+// general double pow() and an order of magnitude cheaper.  pow(0, y>0) = 0 and pow(1, y) = 1
+// short-cut the common cases.
 __device__ __forceinline__ float pow_ref(float x, float y) {
   if (x == 1.0f) return 1.0f;
   if (x == 0.0f && y > 0.0f) return 0.0f;
+  const int n = (int)y;
+  if ((float)n == y && n >= 1 && n <= 256 && x > 0.0f) {
+    double b = (double)x, r = 1.0;
+    for (int k = n; k != 0; k >>= 1) {
+      if (k & 1) r *= b;
+      b *= b;
+    }
+    return (float)r;
+  }
   return (float)pow((double)x, (double)y);
 }
 
