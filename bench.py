@@ -350,7 +350,11 @@ def main():
     gather = BandGather(capi.local_row_map(params), W, H, rank, world, dist, torch, dev) if world > 1 else None
     max_rows = gather.max_rows if gather else rows
     local = torch.zeros((max_rows, W, 4), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: the library replays a captured CUDA graph on it, and the legacy
+    # default stream cannot be captured; everything below (renders, NCCL ops, events) runs on it
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():

@@ -62,11 +62,14 @@ int ensure_device() {
 }
 
 // grow-only device buffer
+long long g_alloc_generation = 0;  // bumped on every (re)allocation: invalidates captured graphs
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return RT_OK;
+    ++g_alloc_generation;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     size_t want = bytes + bytes / 8 + 256;
@@ -129,8 +132,14 @@ struct RtScene {
   // per-frame workspace
   std::vector<LevelStore> levels;
   DevBuf frame_counts;    // FrameCounts
+  DevBuf frame_params;    // FrameParams read by the frame kernels
   DevBuf out_rgba, out_face, out_t, out_rgbf, in_a, in_b;
   FrameCounts *h_counts = nullptr;  // pinned mirror
+  cudaStream_t stream = nullptr;    // used when the caller passes the (uncapturable) legacy default stream
+  // CUDA graph of the bounded-depth frame (memset + every kernel launch), replayed while its key matches
+  cudaGraphExec_t graph_exec = nullptr;
+  std::vector<long long> graph_key;
+  long long ws_generation = 0;      // bumped whenever a workspace buffer is re-allocated
   size_t device_bytes() const {
     return nodes.cap + prims.cap + shade.cap + mats.cap + spheres.cap + sphere_mat.cap + oct_box.cap + oct_face_off.cap +
            oct_face_leaf.cap;
@@ -439,11 +448,12 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
       (rc = upload(sc->spheres, desc->spheres, (size_t)S * 16)) ||
       (rc = upload(sc->sphere_mat, desc->sphere_material, (size_t)S * 4)) ||
       (use_filter && (rc = upload_octree(sc, oct))) ||
-      (rc = sc->frame_counts.reserve(sizeof(FrameCounts)))) {
+      (rc = sc->frame_counts.reserve(sizeof(FrameCounts))) || (rc = sc->frame_params.reserve(sizeof(FrameParams)))) {
     rt_scene_destroy(sc);
     return rc;
   }
-  if (cudaMallocHost((void **)&sc->h_counts, sizeof(FrameCounts)) != cudaSuccess) {
+  if (cudaMallocHost((void **)&sc->h_counts, sizeof(FrameCounts)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) {
     rt_scene_destroy(sc);
     return fail(RT_ERR_CUDA, "cudaMallocHost failed");
   }
@@ -465,7 +475,9 @@ extern "C" void rt_scene_destroy(RtScene *sc) {
   sc->spheres.release(); sc->sphere_mat.release();
   sc->oct_box.release(); sc->oct_face_off.release(); sc->oct_face_leaf.release();
   for (auto &l : sc->levels) l.release();
-  sc->frame_counts.release();
+  sc->frame_counts.release(); sc->frame_params.release();
+  if (sc->graph_exec) cudaGraphExecDestroy(sc->graph_exec);
+  if (sc->stream) cudaStreamDestroy(sc->stream);
   sc->out_rgba.release(); sc->out_face.release(); sc->out_t.release(); sc->out_rgbf.release();
   sc->in_a.release(); sc->in_b.release();
   if (sc->h_counts) cudaFreeHost(sc->h_counts);
@@ -611,43 +623,24 @@ int persistent_grid(K kernel, int block) {
 // Runs the wavefront pipeline.  Level 0 is either generated from the camera (n0 = local pixels)
 // or taken from rays already stored in the level-0 queue buffers (explicit_rays).
 //
-// Bounded depth (max_depth >= 0, <= kAsyncDepth): every level's buffers are sized for n0 rays up
-// front and ray / hit counts stay on the device (FrameCounts), so the whole frame is one stream of
-// launches without a single host read-back.  Unbounded depth (the reference's default) cannot
-// pre-allocate 64 levels, so there the host reads the next level's ray count after each K3 and stops
-// at the first empty level.
+// Bounded depth (0 <= max_depth <= kAsyncDepth): every level's buffers are sized for n0 rays up
+// front, ray / hit counts stay on the device (FrameCounts) and the frame is a fixed sequence
+// "memset, (K1, K2, K3) per level, K3b per level" with no host read-back -- captured once into a CUDA
+// graph and replayed (the per-frame camera / lights / output pointers travel through the FrameParams
+// device buffer, written by k_set_frame just before the replay).
+// Unbounded depth (the reference's default) cannot pre-allocate 64 levels, so there the host reads
+// the next level's ray count after each K3 and stops at the first empty level.
 constexpr int kAsyncDepth = 8;
 
-int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0, uchar4 *d_rgba, int32_t *d_face,
-                 float *d_t, float *d_rgbf, cudaStream_t st, RtStats *stats) {
-  const bool want_stats = stats != nullptr;
-  const bool trav_stats = g_opt_stats != 0;
-  EventTimer timer; timer.on = want_stats; timer.st = st;
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-  if (want_stats) { cudaEventCreate(&ev_a); cudaEventCreate(&ev_b); cudaEventRecord(ev_a, st); }
+struct FramePlan {
+  bool explicit_rays, trav_stats, async;
+  int n0, J, Lmax, S, depth_cap, refill;
+};
 
-  const int Lmax = std::max(1, fp.n_lights);
-  const int S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
-  const int J = Lmax + Lmax * S;
-  if ((unsigned long long)n0 * (unsigned long long)J >= 0xffffffffull)
-    return fail(RT_ERR_LIMIT, "%d rays x %d shadow jobs exceed 2^32; render the frame in bands", n0, J);
-  const bool async = fp.max_depth >= 0 && fp.max_depth <= kAsyncDepth;
-  const int depth_cap = fp.max_depth >= 0 ? fp.max_depth : fp.guard_depth;
-  if (depth_cap + 2 > RT_MAX_LEVELS) return fail(RT_ERR_LIMIT, "max_depth %d too large", fp.max_depth);
-
+// enqueue the launches of levels [0, depth_cap] and the folds (async mode: all of them)
+int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *launches) {
+  const FrameParams *fpp = sc->frame_params.as<FrameParams>();
   FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
-  CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
-  int launches = 0, rc;
-
-  if (async) {
-    if ((int)sc->levels.size() < depth_cap + 2) sc->levels.resize(depth_cap + 2);
-    for (int l = 0; l <= depth_cap; ++l)
-      if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)J))) return rc;
-  } else {
-    if (sc->levels.empty()) sc->levels.resize(1);
-    if ((rc = sc->levels[0].reserve((size_t)n0, (size_t)J))) return rc;
-  }
-
   static int grid_k1p = 0, grid_k1s = 0, grid_k2 = 0, grid_k1p_s = 0, grid_k1s_s = 0, grid_k2_s = 0;
   if (!grid_k1p) {
     grid_k1p = persistent_grid(k_trace_nearest<true, false>, 128);
@@ -657,61 +650,152 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
     grid_k1s_s = persistent_grid(k_trace_nearest<false, true>, 128);
     grid_k2_s = persistent_grid(k_shadow<true>, 128);
   }
-  const int elem_blocks = std::max(1, std::min((n0 + 127) / 128, g_sm_count * 16));
+  const int elem_blocks = std::max(1, std::min((pl.n0 + 127) / 128, g_sm_count * 16));
+  CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
+  for (int level = 0; level <= pl.depth_cap; ++level) {
+    LevelBufs lv = sc->levels[level].bufs();
+    LevelBufs nx = sc->levels[level + 1].bufs();
+    const int n_param = level == 0 ? pl.n0 : -1;
+    if (level == 0 && !pl.explicit_rays) {
+      if (pl.trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+    } else {
+      if (pl.trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+    }
+    if (pl.trav_stats) k_shadow<true><<<grid_k2_s, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
+    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
+    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc);
+    *launches += 3;
+  }
+  for (int level = pl.depth_cap - 1; level >= 0; --level) {
+    k_fold<<<elem_blocks, 256, 0, st>>>(fpp, sc->levels[level].bufs(), sc->levels[level + 1].bufs(), level,
+                                        level == 0 ? pl.n0 : -1, fc);
+    *launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return RT_OK;
+}
 
+int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int n0, uchar4 *d_rgba, int32_t *d_face,
+                 float *d_t, float *d_rgbf, cudaStream_t user_stream, RtStats *stats) {
+  // the legacy default stream cannot be captured: run on the scene's own stream and join at the end
+  const bool own_stream = user_stream == nullptr;
+  cudaStream_t st = own_stream ? sc->stream : user_stream;
+  if (own_stream) CUDA_TRY(cudaDeviceSynchronize());  // order after whatever the caller queued on stream 0
+
+  FrameParams fp = fp_in;
+  fp.out_rgba = d_rgba; fp.out_face = d_face; fp.out_t = d_t; fp.out_rgbf = d_rgbf;
+
+  const bool want_stats = stats != nullptr;
+  FramePlan pl;
+  pl.explicit_rays = explicit_rays;
+  pl.trav_stats = g_opt_stats != 0;
+  pl.n0 = n0;
+  pl.Lmax = std::max(1, fp.n_lights);
+  pl.S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
+  pl.J = pl.Lmax + pl.Lmax * pl.S;
+  pl.refill = g_opt_refill_below;
+  if ((unsigned long long)n0 * (unsigned long long)pl.J >= 0xffffffffull)
+    return fail(RT_ERR_LIMIT, "%d rays x %d shadow jobs exceed 2^32; render the frame in bands", n0, pl.J);
+  pl.async = fp.max_depth >= 0 && fp.max_depth <= kAsyncDepth;
+  pl.depth_cap = fp.max_depth >= 0 ? fp.max_depth : fp.guard_depth;
+  if (pl.depth_cap + 2 > RT_MAX_LEVELS) return fail(RT_ERR_LIMIT, "max_depth %d too large", fp.max_depth);
+
+  EventTimer timer; timer.on = want_stats; timer.st = st;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  if (want_stats) { cudaEventCreate(&ev_a); cudaEventCreate(&ev_b); cudaEventRecord(ev_a, st); }
+
+  FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
+  FrameParams *fpp = sc->frame_params.as<FrameParams>();
+  int launches = 0, rc;
+  k_set_frame<<<1, 128, 0, st>>>(fp, fpp);
+  ++launches;
+
+  if (pl.async && !want_stats) {
+    // ---- bounded depth: CUDA graph replay ----
+    if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
+    for (int l = 0; l <= pl.depth_cap; ++l)
+      if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
+    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.refill,
+                                        (long long)pl.explicit_rays, (long long)pl.trav_stats};
+    if (sc->graph_exec == nullptr || key != sc->graph_key) {
+      if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_frame_async(sc, pl, st, &launches);
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&sc->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { sc->graph_exec = nullptr; return fail(RT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+      sc->graph_key = key;
+    }
+    CUDA_TRY(cudaGraphLaunch(sc->graph_exec, st));
+    if (own_stream) CUDA_TRY(cudaStreamSynchronize(st));
+    return RT_OK;
+  }
+
+  // ---- stream launches (statistics requested, or unbounded depth with host-visible ray counts) ----
+  if (pl.async) {
+    if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
+    for (int l = 0; l <= pl.depth_cap; ++l)
+      if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
+  } else {
+    if (sc->levels.size() < 2) sc->levels.resize(2);
+    if ((rc = sc->levels[0].reserve((size_t)n0, (size_t)pl.J))) return rc;
+  }
+  CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
+  static int g1p = 0, g1s = 0, g2 = 0, g1ps = 0, g1ss = 0, g2s = 0;
+  if (!g1p) {
+    g1p = persistent_grid(k_trace_nearest<true, false>, 128); g1s = persistent_grid(k_trace_nearest<false, false>, 128);
+    g2 = persistent_grid(k_shadow<false>, 128); g1ps = persistent_grid(k_trace_nearest<true, true>, 128);
+    g1ss = persistent_grid(k_trace_nearest<false, true>, 128); g2s = persistent_grid(k_shadow<true>, 128);
+  }
+  const int elem_blocks = std::max(1, std::min((n0 + 127) / 128, g_sm_count * 16));
   int levels_run = 0;
   int cur_n = n0;  // host knowledge of the level's ray count (exact in sync mode, upper bound in async mode)
-  for (int level = 0; level <= depth_cap; ++level) {
+  for (int level = 0; level <= pl.depth_cap; ++level) {
     LevelBufs lv = sc->levels[level].bufs();
     const int n_param = level == 0 ? n0 : -1;
-    // ---- K1 ----
     timer.begin(0);
     if (level == 0 && !explicit_rays) {
-      if (trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf, g_opt_refill_below);
-      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, d_face, d_t, d_rgba, d_rgbf, g_opt_refill_below);
+      if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      else k_trace_nearest<true, false><<<g1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
     } else {
-      uchar4 *fb0 = level == 0 ? d_rgba : nullptr;
-      float *rgbf0 = level == 0 ? d_rgbf : nullptr;
-      int32_t *face0 = level == 0 ? d_face : nullptr;
-      float *t0 = level == 0 ? d_t : nullptr;
-      if (trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0, g_opt_refill_below);
-      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fp, lv, level, n_param, fc, face0, t0, fb0, rgbf0, g_opt_refill_below);
+      if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      else k_trace_nearest<false, false><<<g1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
     }
     timer.end();
-    // ---- K2 ----
     timer.begin(1);
-    if (trav_stats) k_shadow<true><<<grid_k2_s, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc, g_opt_refill_below);
-    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fp, lv, level, J, Lmax, S, fc, g_opt_refill_below);
+    if (pl.trav_stats) k_shadow<true><<<g2s, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
+    else k_shadow<false><<<g2, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
     timer.end();
-    // ---- K3 ----
-    const bool may_spawn = level < depth_cap;
-    if (!async) {
+    const bool may_spawn = level < pl.depth_cap;
+    if (!pl.async) {
       if ((int)sc->levels.size() < level + 2) sc->levels.resize(level + 2);
-      if (may_spawn && (rc = sc->levels[level + 1].reserve((size_t)cur_n, (size_t)J))) return rc;
+      if (may_spawn && (rc = sc->levels[level + 1].reserve((size_t)cur_n, (size_t)pl.J))) return rc;
     }
     LevelBufs nx = sc->levels[std::min(level + 1, (int)sc->levels.size() - 1)].bufs();
     timer.begin(2);
-    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fp, lv, nx, level, J, Lmax, S, fc, level == 0 ? d_rgba : nullptr,
-                                         level == 0 ? d_rgbf : nullptr);
+    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc);
     timer.end();
     launches += 3;
     levels_run = level + 1;
     CUDA_TRY(cudaGetLastError());
     if (!may_spawn) break;
-    if (!async) {
+    if (!pl.async) {
       CUDA_TRY(cudaMemcpyAsync(&sc->h_counts->n_rays[level + 1], &fc->n_rays[level + 1], 4, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       cur_n = sc->h_counts->n_rays[level + 1];
       if (cur_n <= 0) break;
     }
   }
-  // ---- K3b: fold deepest-first ----
   for (int level = levels_run - 2; level >= 0; --level) {
-    LevelBufs lv = sc->levels[level].bufs();
-    LevelBufs nx = sc->levels[level + 1].bufs();
     timer.begin(2);
-    k_fold<<<elem_blocks, 256, 0, st>>>(fp, lv, nx, level, level == 0 ? n0 : -1, fc, level == 0 ? d_rgba : nullptr,
-                                        level == 0 ? d_rgbf : nullptr);
+    k_fold<<<elem_blocks, 256, 0, st>>>(fpp, sc->levels[level].bufs(), sc->levels[level + 1].bufs(), level,
+                                        level == 0 ? n0 : -1, fc);
     timer.end();
     ++launches;
   }
@@ -746,6 +830,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp, bool explicit_rays, int n0,
     stats->filter_slow = (int64_t)h.ctr.filter_slow;
     stats->filter_rejects = (int64_t)h.ctr.filter_rejects;
   }
+  if (own_stream) CUDA_TRY(cudaStreamSynchronize(st));
   return RT_OK;
 }
 

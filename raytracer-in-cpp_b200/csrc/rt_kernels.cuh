@@ -96,10 +96,14 @@ __device__ __forceinline__ unsigned long long pool_batch(unsigned long long n_it
 }
 
 template <bool PRIMARY, bool STATS>
-__global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const FrameParams fp, const LevelBufs lv,
-                                                      const int level, const int n0, FrameCounts *fc,
-                                                      int32_t *face_out, float *t_out, uchar4 *fb, float *rgb_f32,
-                                                      const int refill_below) {
+__global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const FrameParams *__restrict__ fpp,
+                                                      const LevelBufs lv, const int level, const int n0,
+                                                      FrameCounts *fc, const int refill_below) {
+  RT_STAGE_FRAME_PARAMS(fpp);
+  int32_t *face_out = level == 0 ? fp.out_face : nullptr;
+  float *t_out = level == 0 ? fp.out_t : nullptr;
+  uchar4 *fb = level == 0 ? fp.out_rgba : nullptr;
+  float *rgb_f32 = level == 0 ? fp.out_rgbf : nullptr;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of work items (warp-uniform)
@@ -276,9 +280,10 @@ __device__ __forceinline__ V3 area_sample(const FrameParams &fp, V3 c, int k) {
 // Each warp takes 4 x 32 jobs per cursor update to keep the atomic off the critical path.
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FrameParams fp, const LevelBufs lv,
-                                               const int level, const int J, const int Lmax, const int S,
-                                               FrameCounts *fc, const int refill_below) {
+__global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FrameParams *__restrict__ fpp,
+                                               const LevelBufs lv, const int level, const int J, const int Lmax,
+                                               const int S, FrameCounts *fc, const int refill_below) {
+  RT_STAGE_FRAME_PARAMS(fpp);
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of jobs (warp-uniform)
@@ -497,9 +502,12 @@ __device__ __forceinline__ V3 phong_sample(V3 Ikd, V3 Iks, float shininess, V3 h
 // K3: shade one bounce level.  One thread per ray that hit (hit_list slot); warps stay converged
 // around the queue append (ballot + popc, one atomic per warp).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FrameParams fp, const LevelBufs lv,
-                                              const LevelBufs nx, const int level, const int J, const int Lmax,
-                                              const int S, FrameCounts *fc, uchar4 *fb, float *rgb_f32) {
+__global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FrameParams *__restrict__ fpp,
+                                              const LevelBufs lv, const LevelBufs nx, const int level, const int J,
+                                              const int Lmax, const int S, FrameCounts *fc) {
+  RT_STAGE_FRAME_PARAMS(fpp);
+  uchar4 *fb = level == 0 ? fp.out_rgba : nullptr;
+  float *rgb_f32 = level == 0 ? fp.out_rgbf : nullptr;
   const int n_hits = fc->n_hits[level];
   const int n_round = (n_hits + 31) & ~31;
   unsigned samples_shaded = 0;
@@ -602,8 +610,11 @@ __global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FramePar
 // ---------------------------------------------------------------------------------------------
 // K3b: fold level k from level k+1 (deepest first); level 0 writes the framebuffer.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fold(const FrameParams fp, const LevelBufs lv, const LevelBufs nx, const int level,
-                                             const int n0, const FrameCounts *fc, uchar4 *fb, float *rgb_f32) {
+__global__ void __launch_bounds__(256) k_fold(const FrameParams *__restrict__ fpp, const LevelBufs lv, const LevelBufs nx,
+                                             const int level, const int n0, const FrameCounts *fc) {
+  RT_STAGE_FRAME_PARAMS(fpp);
+  uchar4 *fb = level == 0 ? fp.out_rgba : nullptr;
+  float *rgb_f32 = level == 0 ? fp.out_rgbf : nullptr;
   const int n = n0 >= 0 ? n0 : fc->n_rays[level];
   if (fc->n_rays[level + 1] == 0) return;  // nothing was spawned below this level
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -618,6 +629,13 @@ __global__ void __launch_bounds__(256) k_fold(const FrameParams fp, const LevelB
       if (rgb_f32) { rgb_f32[3 * (size_t)i] = col.x; rgb_f32[3 * (size_t)i + 1] = col.y; rgb_f32[3 * (size_t)i + 2] = col.z; }
     }
   }
+}
+
+// writes the frame parameters (passed by value at launch) into their device buffer
+__global__ void k_set_frame(const FrameParams fp, FrameParams *dst) {
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(&fp);
+  uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+  for (int w = threadIdx.x; w < (int)(sizeof(FrameParams) / 4); w += blockDim.x) d[w] = src[w];
 }
 
 // ---------------------------------------------------------------------------------------------
