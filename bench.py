@@ -535,11 +535,18 @@ def main():
     w_alg = 16.0 * (stats["box_tests"] + stats["box_tests_shadow"]) + 40.0 * (stats["tri_tests"] + stats["tri_tests_shadow"]) \
         + 120.0 * stats["shade_samples"]
     frame_ms_1gpu = ms_per_step
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    kname = {"trace": "k_trace_nearest", "shadow": "k_shadow", "shade": "k_shade"}[dom]
+    if world == 1 and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(kname)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": {"trace": "k_trace_nearest", "shadow": "k_shadow", "shade": "k_shade"}[dom],
+                "traffic": traffic, "kernel": kname,
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "cache-level algorithmic bytes (32 B/box test, 48 B/triangle test); the path is SM-issue "
-                        "bound, see sm_issue",
+                "note": "achieved = cache-level ALGORITHMIC bytes (32 B per ray-AABB test, 48 B per ray-triangle test, "
+                        "SURVEY.md 8d) of the dominant kernel / its CUDA-event duration; traffic = measured DRAM bytes of "
+                        "that kernel (ncu --set full, profiles/r01_traffic.json): the working set is served by L1/L2, "
+                        "the path is SM-issue bound, see sm_issue",
                 "sm_issue": {"achieved_thread_instr_per_s": w_alg / (frame_ms_1gpu * 1e-3),
                              "peak_thread_instr_per_s": issue_peak, "frac": w_alg / (frame_ms_1gpu * 1e-3) / issue_peak,
                              "model": "16*N_box + 40*N_tri + 120*N_samples over the whole frame (rank 0's share)"}}
