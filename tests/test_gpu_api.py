@@ -290,3 +290,80 @@ def test_analytic_spheres_match_the_port(area, point, depth, pkg, oracle_mod, sc
     exp = np.clip(O.quantize(rgb), 0, 255)
     err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - exp).max(-1)
     assert err.max() <= 1 and (err == 0).mean() > 0.999, f"max err {err.max()}, exact {(err == 0).mean()}"
+
+
+def test_plain_bvh_mode_is_the_exact_nearest_hit(pkg, oracle_mod, scene_dir):
+    """rt_set_option("reference_candidates", 0): without the octree filter the BVH returns the nearest
+    hit over ALL faces, i.e. the oracle in brute-force candidate mode -- including the centre row of the
+    image where the reference itself has holes (rays in an octree split plane)."""
+    O = oracle_mod
+    capi = pkg.capi
+    capi.init(0)
+    case = "hf224_point_3840x2160_s24"
+    g = load_golden(case)
+    arrs = scene_arrays(case, pkg, scene_dir)
+    capi.set_option("reference_candidates", 0)
+    try:
+        scene = capi.Scene(*arrs)
+    finally:
+        capi.set_option("reference_candidates", 1)
+    W, H = 480, 270  # even height: row 135 has dir.y == 0
+    cam = capi.default_camera(W, H)
+    lights = capi.Lights(g["lights"])
+    fr = scene.render(cam, lights, capi.make_params(W, H, 0, 1, 0))
+    orc = O.Oracle(O.BakedScene(*arrs), area=0, point=1, max_depth=0, candidates=1)
+    ocam = O.Oracle.camera((0, 0, 2), np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2]], np.float32), (0, 0, W, H), 60.0,
+                           np.float32(W) / np.float32(H))
+    ys = np.array([100, 134, 135, 136, 200], np.int32)
+    xs = np.arange(0, W, 1, dtype=np.int32)
+    pxy = np.stack(np.meshgrid(xs, ys, indexing="ij"), -1).reshape(-1, 2)
+    rgb, face, t, rgb8 = orc.render_pixels(ocam, g["lights"], pxy, threads=8)
+    assert (fr.face[pxy[:, 1], pxy[:, 0]] == face).all()
+    assert (fr.t[pxy[:, 1], pxy[:, 0]].view(np.uint32) == t.view(np.uint32)).all()
+    # and with the filter on, the same rows match the faithful (octree) oracle instead
+    scene2 = capi.Scene(*arrs)
+    fr2 = scene2.render(cam, lights, capi.make_params(W, H, 0, 1, 0))
+    orc2 = O.Oracle(O.BakedScene(*arrs), area=0, point=1, max_depth=0, candidates=0)
+    rgb2, face2, t2, _ = orc2.render_pixels(ocam, g["lights"], pxy, threads=8)
+    assert (fr2.face[pxy[:, 1], pxy[:, 0]] == face2).all()
+    print(f"plain BVH vs filtered: {(face != face2).sum()} of {len(face)} sampled pixels differ (reference octree holes)")
+
+
+@pytest.mark.parametrize("refill", [8, 24])
+def test_dynamic_fetch_gives_identical_frames(refill, pkg, scene_dir):
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("gallery_area_200x150")
+    arrs = scene_arrays("gallery_area_200x150", pkg, scene_dir)
+    scene = capi.Scene(*arrs)
+    cam = capi.default_camera(200, 150)
+    lights = capi.Lights(g["lights"])
+    p = capi.make_params(200, 150, 1, 0, 3, (4, 4))
+    a = scene.render(cam, lights, p)
+    capi.set_option("refill_below", refill)
+    try:
+        b = scene.render(cam, lights, p)
+    finally:
+        capi.set_option("refill_below", 0)
+    assert (a.rgba == b.rgba).all() and (a.face == b.face).all() and (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
+
+
+def test_unbounded_depth_matches_bounded_when_cap_is_large(pkg, scene_dir):
+    """max_depth < 0 (the reference's unbounded recursion, host-synchronised level loop) and a cap
+    larger than the scene's natural depth (CUDA-graph path) must give the same frame."""
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("gallery_small_point_320x240")
+    arrs = scene_arrays("gallery_small_point_320x240", pkg, scene_dir)
+    scene = capi.Scene(*arrs)
+    cam = capi.default_camera(160, 120)
+    lights = capi.Lights(g["lights"])
+    a = scene.render(cam, lights, capi.make_params(160, 120, 0, 1, -1))
+    levels = a.stats["levels"]
+    assert levels <= 8, levels
+    b = scene.render(cam, lights, capi.make_params(160, 120, 0, 1, 8))
+    assert (a.rgba == b.rgba).all()
+    # repeated graph replays are stable
+    for _ in range(3):
+        c = scene.render(cam, lights, capi.make_params(160, 120, 0, 1, 8), want_stats=False)
+        assert (c.rgba == b.rgba).all()
