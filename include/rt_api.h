@@ -136,7 +136,8 @@ int rt_device_name(char *buf, size_t n);
  * reference's octree candidate sets so that the image matches the reference bit for bit; 0: plain
  * BVH = exact nearest hit over all faces), "refill_below" (dynamic ray fetch: persistent warps hand new
  * rays to their idle lanes once fewer than this many lanes are still traversing; 0 = only when all
- * 32 are done) */
+ * 32 are done), "shadow_packets" (0, default: every shadow ray is traced on its own; 1: the
+ * area-light sample rays of a hit are traced as lockstep packets when the BVH has >= 64 nodes; 2: always) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);
 

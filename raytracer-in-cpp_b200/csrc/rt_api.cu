@@ -34,9 +34,10 @@ thread_local std::string g_err;
 int g_device = -1;
 int g_sm_count = 0;
 int g_opt_stats = 0;
-int g_opt_leaf = 4;
+int g_opt_leaf = 2;  // measured best on the 100 k / 1 M-triangle scenes (leaf tests are exact and expensive)
 int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
 int g_opt_ref_candidates = 1;
+int g_opt_shadow_packets = 0;  // 1/2: area-light sample rays traced as lockstep packets (measured slower)
 int g_opt_refill_below = 0;  // dynamic fetch: refill a warp when fewer lanes than this still traverse (0 = when all are done)
 
 int fail(int code, const char *fmt, ...) {
@@ -188,6 +189,7 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
   else if (!strcmp(key, "reference_candidates")) g_opt_ref_candidates = value ? 1 : 0;
   else if (!strcmp(key, "refill_below")) g_opt_refill_below = std::max(0, std::min(32, value));
+  else if (!strcmp(key, "shadow_packets")) g_opt_shadow_packets = std::max(0, std::min(2, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
 }
@@ -635,7 +637,22 @@ constexpr int kAsyncDepth = 8;
 struct FramePlan {
   bool explicit_rays, trav_stats, async;
   int n0, J, Lmax, S, depth_cap, refill;
+  int packet_group;  // 0: every shadow ray through k_shadow; 16 / 32: sample rays as packets of that many lanes
 };
+
+// K2 for one level: gate + sample rays per ray, or gate rays per ray + sample rays as packets
+void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, const LevelBufs &lv, int level, FrameCounts *fc,
+                   cudaStream_t st, int grid, int *launches) {
+  const int jobs = pl.packet_group ? pl.Lmax : pl.J;
+  if (pl.trav_stats) k_shadow<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc, pl.refill);
+  else k_shadow<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc, pl.refill);
+  *launches += 1;
+  if (pl.packet_group) {
+    if (pl.trav_stats) k_shadow_packet<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, pl.packet_group, fc);
+    else k_shadow_packet<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, pl.packet_group, fc);
+    *launches += 1;
+  }
+}
 
 // enqueue the launches of levels [0, depth_cap] and the folds (async mode: all of them)
 int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *launches) {
@@ -663,10 +680,9 @@ int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *
       if (pl.trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
       else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
     }
-    if (pl.trav_stats) k_shadow<true><<<grid_k2_s, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
-    else k_shadow<false><<<grid_k2, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
+    launch_shadow(sc, pl, fpp, lv, level, fc, st, pl.trav_stats ? grid_k2_s : grid_k2, launches);
     k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc);
-    *launches += 3;
+    *launches += 2;
   }
   for (int level = pl.depth_cap - 1; level >= 0; --level) {
     k_fold<<<elem_blocks, 256, 0, st>>>(fpp, sc->levels[level].bufs(), sc->levels[level + 1].bufs(), level,
@@ -696,6 +712,9 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
   pl.S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
   pl.J = pl.Lmax + pl.Lmax * pl.S;
   pl.refill = g_opt_refill_below;
+  // packets pay off when rays actually walk a tree; on a handful of nodes the per-ray kernel is already converged
+  pl.packet_group = 0;
+  if (g_opt_shadow_packets && pl.S >= 4 && (sc->dev.n_nodes >= 64 || g_opt_shadow_packets == 2)) pl.packet_group = pl.S <= 16 ? 16 : 32;
   if ((unsigned long long)n0 * (unsigned long long)pl.J >= 0xffffffffull)
     return fail(RT_ERR_LIMIT, "%d rays x %d shadow jobs exceed 2^32; render the frame in bands", n0, pl.J);
   pl.async = fp.max_depth >= 0 && fp.max_depth <= kAsyncDepth;
@@ -717,7 +736,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
     for (int l = 0; l <= pl.depth_cap; ++l)
       if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
-    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.refill,
+    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.refill, pl.packet_group,
                                         (long long)pl.explicit_rays, (long long)pl.trav_stats};
     if (sc->graph_exec == nullptr || key != sc->graph_key) {
       if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
@@ -769,8 +788,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     }
     timer.end();
     timer.begin(1);
-    if (pl.trav_stats) k_shadow<true><<<g2s, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
-    else k_shadow<false><<<g2, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, pl.refill);
+    launch_shadow(sc, pl, fpp, lv, level, fc, st, pl.trav_stats ? g2s : g2, &launches);
     timer.end();
     const bool may_spawn = level < pl.depth_cap;
     if (!pl.async) {
@@ -781,7 +799,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     timer.begin(2);
     k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc);
     timer.end();
-    launches += 3;
+    launches += 2;
     levels_run = level + 1;
     CUDA_TRY(cudaGetLastError());
     if (!may_spawn) break;

@@ -367,3 +367,25 @@ def test_unbounded_depth_matches_bounded_when_cap_is_large(pkg, scene_dir):
     for _ in range(3):
         c = scene.render(cam, lights, capi.make_params(160, 120, 0, 1, 8), want_stats=False)
         assert (c.rgba == b.rgba).all()
+
+
+def test_shadow_packets_give_identical_frames(pkg, scene_dir):
+    """The optional packet traversal of area-light sample rays (k_shadow_packet) is a pure scheduling
+    change: same visibility bits, same frame."""
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("gallery_area_200x150")
+    arrs = scene_arrays("gallery_area_200x150", pkg, scene_dir)
+    scene = capi.Scene(*arrs)
+    cam = capi.default_camera(200, 150)
+    lights = capi.Lights(g["lights"])
+    for grid in [(4, 4), (5, 5), (3, 2)]:
+        p = capi.make_params(200, 150, 1, 0, 3, grid)
+        a = scene.render(cam, lights, p)
+        capi.set_option("shadow_packets", 2)
+        try:
+            b = scene.render(cam, lights, p)
+        finally:
+            capi.set_option("shadow_packets", 0)
+        assert (a.rgba == b.rgba).all() and (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
+        assert a.stats["rays_shadow"] == b.stats["rays_shadow"]
