@@ -57,6 +57,19 @@ def build_cli(force: bool = False) -> str:
     return CLI
 
 
+PROBE = os.path.join(HERE, "facade_probe")
+
+
+def build_probe(force: bool = False) -> str:
+    """Small C++ program that calls every render-path member of the facade once (used by the GPU tests)."""
+    srcs = ["host/facade_probe.cpp", "host/flyscene.cpp"]
+    if force or _stale(PROBE, srcs + ["host/flyscene.hpp", "librt_b200.so"]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-o", PROBE] + srcs +
+                              ["-L" + HERE, "-lrt_b200", "-Wl,-rpath,$ORIGIN"], cwd=HERE)
+    return PROBE
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_cli(force)
+    build_probe(force)

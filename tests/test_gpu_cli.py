@@ -73,3 +73,55 @@ def test_cli_on_generated_scene_matches_oracle(pkg, oracle_mod, tmp_path):
     exp = np.clip(O.quantize(rgb), 0, 255)
     err = np.abs(img[pxy[:, 1], pxy[:, 0]] - exp).max(-1)
     assert (err <= 1).mean() >= 0.999 and err.max() <= 1, f"max err {err.max()}"
+
+
+def test_cpp_facade_members_match_oracle(pkg, oracle_mod, tmp_path):
+    """Every render-path member of the C++ facade (Flyscene / BoxTree / BoundingBox / arealight /
+    Flycamera), called the way the reference's debug-ray tool calls them, against the oracle."""
+    import ctypes as C
+    O = oracle_mod
+    probe = pkg.build.build_probe()
+    obj = str(tmp_path / "gallery.obj")
+    pkg.scenes.write_gallery(obj, 3)
+    px, py = 300.0, 260.0
+    r = subprocess.run([probe, obj, str(px), str(py)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout[r.stdout.index("{"):])
+    mesh = pkg.capi.Mesh(obj)
+    arrs = mesh.arrays()
+    orc = O.Oracle(O.BakedScene(*arrs), area=1, point=0, max_depth=2, grid=(5, 5))
+    W, H = 640, 480
+    cam = O.Oracle.camera((0, 0, 2), np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2]], np.float32), (0, 0, W, H), 60.0,
+                          np.float32(W) / np.float32(H))
+    f32 = lambda v: np.array(v, np.float32)
+    screen = np.zeros(3, np.float32)
+    O.lib().or_screen_to_world(cam, px, py, screen.ctypes.data)
+    assert (f32(out["screen"]) == screen).all() and out["origin"] == [0, 0, 2]
+    assert out["faces"] == arrs[0].shape[0]
+    mn, mx = orc.root_box()
+    assert (f32(out["root_min"]) == mn).all() and (f32(out["root_max"]) == mx).all()
+    origin = f32([0, 0, 2])
+    d = (screen - origin).astype(np.float32)
+    dest = (d + origin).astype(np.float32)
+    ids = np.zeros(arrs[0].shape[0], np.int32)
+    n = O.lib().or_octree_candidates(orc.handle, origin.ctypes.data, dest.ctypes.data, ids.ctypes.data, len(ids))
+    assert out["candidates"] == n and out["candidate_sum"] == int(ids[:n].astype(np.int64).sum())
+    lights = np.array([[-1, 1, 1], [1.5, 1.0, 1.0]], np.float32)
+    rgb = np.zeros(3, np.float32); face = np.zeros(1, np.int32); t = np.zeros(1, np.float32)
+    O.lib().or_trace_ray(orc.handle, origin.ctypes.data, d.ctypes.data, 0, lights.ctypes.data, 2, rgb.ctypes.data,
+                         face.ctypes.data, t.ctypes.data)
+    assert out["best"] == int(face[0]) and np.float32(out["t"]) == t[0]
+    assert np.allclose(f32(out["colour"]), rgb, rtol=2e-6, atol=1e-7)
+    if face[0] >= 0:
+        hit = (origin + t[0] * d).astype(np.float32)
+        vis = np.zeros(2, np.uint8)
+        anyv = O.lib().or_light_strikes(orc.handle, hit.ctypes.data, lights.ctypes.data, 2, vis.ctypes.data)
+        assert out["light_any"] == anyv and out["light_vis"] == [int(vis[0]), int(vis[1])]
+        ph = np.zeros(3, np.float32)
+        O.lib().or_phong_shade(orc.handle, origin.ctypes.data, hit.ctypes.data, int(face[0]), lights.ctypes.data, 2, ph.ctypes.data)
+        assert np.allclose(f32(out["phong"]), ph, rtol=2e-6, atol=1e-7)
+    assert out["n_samples"] == 25
+    assert np.allclose(out["sample0"], (-0.0700000003, 0.114999995, 1), atol=1e-8)
+    assert np.allclose(out["sample24"], (-0.629999995, 1.03499997, 1), atol=1e-8)
+    assert out["bb_hit"] == 1 and out["bb_miss"] == 0
+    assert out["octree"] == [int(x) for x in orc.octree_stats()]
