@@ -653,7 +653,7 @@ __device__ __forceinline__ V3 phong_sample(V3 Ikd, V3 Iks, float shininess, V3 h
 // K3: shade one bounce level.  One thread per ray that hit (hit_list slot); warps stay converged
 // around the queue append (ballot + popc, one atomic per warp).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(const DevScene sc, const FrameParams *__restrict__ fpp,
+__global__ void __launch_bounds__(128, 8) k_shade(const DevScene sc, const FrameParams *__restrict__ fpp,
                                               const LevelBufs lv, const LevelBufs nx, const int level, const int J,
                                               const int Lmax, const int S, FrameCounts *fc) {
   RT_STAGE_FRAME_PARAMS(fpp);
