@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const 
           int i;
           bool valid;
           V3 o, d;
+          V3 screen = mk(0.f, 0.f, 0.f);
           bool tri_enabled = true;
           if constexpr (PRIMARY) {
             const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
@@ -186,10 +187,7 @@ __global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const 
             o = ld3(fp.eye);
             d = mk(0.f, 0.f, 0.f);
             if (valid) {
-              const V3 screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
-              // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
-              // (scenes with analytic spheres -- not a reference feature -- skip it, like rt_oracle.c)
-              tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, o, screen) || sc.n_spheres > 0;
+              screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
               d = sub(screen, o);  // :619, not normalised
             }
           } else {
@@ -199,11 +197,18 @@ __global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const 
             o = mk(ro); d = mk(rd);
           }
           if (valid) {
+            // one exact reciprocal of the direction serves both root-box tests and the traversal
+            const V3 rdir = recip_dir(d);
+            if constexpr (PRIMARY) {
+              // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
+              // (scenes with analytic spheres -- not a reference feature -- skip it, like rt_oracle.c)
+              tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || sc.n_spheres > 0;
+            }
             // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
             const V3 dest = add(o, d);
-            tri_enabled = tri_enabled && ref_box_intersect(sc.root_min, sc.root_max, o, dest);
+            tri_enabled = tri_enabled && ref_box_intersect_quick(sc.root_min, sc.root_max, o, dest, rdir);
             cur_i = i;
-            tr.init(o, d, dest, tri_enabled);
+            tr.init(o, d, dest, tri_enabled, rdir);
             if (tri_enabled || sc.n_spheres > 0) {
               active = true;
             } else {
@@ -343,10 +348,11 @@ __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FramePa
             const V3 o = mk(ro), d = mk(rd);
             const V3 hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
             const V3 sd = sub(hit, src);                 // :920
-            const bool tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);  // :924
+            const V3 rdir = recip_dir(sd);
+            const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, hit, rdir);  // :924
             traced++;
             if (tri_enabled || sc.n_spheres > 0) {
-              tr.init(src, sd, hit, tri_enabled);
+              tr.init(src, sd, hit, tri_enabled, rdir);
               cur_g = g;
               active = true;
             } else {
