@@ -586,6 +586,25 @@ int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, con
   fp.area_len_x = p->area_len_x; fp.area_len_y = p->area_len_y;
   fp.max_depth = p->max_depth;
   fp.guard_depth = 64;
+  // area-light sample table for the scene lights (same expression as the device's area_sample)
+  fp.have_sample_table = 0;
+  if (!p->point_light && p->area_light) {
+    const int S = p->usteps * p->vsteps;
+    if (lights->n * S <= RT_SAMPLE_TABLE) {
+      for (int l = 0; l < lights->n; ++l) {
+        const float *c = lights->pos + 3 * l;
+        const float ux = c[0] + p->area_len_x * 1.0f, vy = c[1] + p->area_len_y * 1.0f, uz = c[2] + p->area_len_x * 0.0f;
+        for (int k = 0; k < S; ++k) {
+          const int i = k / p->vsteps, j = k - i * p->vsteps;
+          float *q = fp.sample_table + 3 * (l * S + k);
+          q[0] = (float)((double)i + 0.5) * (ux / (float)p->usteps);
+          q[1] = (float)((double)j + 0.5) * (vy / (float)p->vsteps);
+          q[2] = uz;
+        }
+      }
+      fp.have_sample_table = 1;
+    }
+  }
   return RT_OK;
 }
 

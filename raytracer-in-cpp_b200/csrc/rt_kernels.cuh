@@ -277,6 +277,13 @@ __device__ __forceinline__ V3 area_sample(const FrameParams &fp, V3 c, int k) {
   return mk(sx, sy, uz);
 }
 
+// sample s of light l as seen by a ray: from the per-frame table for scene lights, computed for the
+// single inherited light of mirror children
+__device__ __forceinline__ V3 light_sample(const FrameParams &fp, const RayLights &rl, int l, int s, int S) {
+  if (!rl.single && fp.have_sample_table) return ld3(fp.sample_table + 3 * (l * S + s));
+  return area_sample(fp, light_pos(fp, rl, l), s);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: shadow rays for the rays of hit_list.  Job g = slot * J + j;  j < Lmax: gate ray towards light j
 // (:699);  j >= Lmax: sample ray (light (j-Lmax)/S, sample (j-Lmax)%S) of phongShade's lightStrikes
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FramePa
           } else {
             const int s = j - Lmax;
             l = s / S;
-            if (l >= rl.n) have = false; else src = area_sample(fp, light_pos(fp, rl, l), s - l * S);
+            if (l >= rl.n) have = false; else src = light_sample(fp, rl, l, s - l * S, S);
           }
           if (!have) {
             lv.vis[g] = 0;
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(128) k_shadow_packet(const DevScene sc, const 
         lv.vis[vis_index] = 0;
       } else {
         have_job = true;
-        src = area_sample(fp, light_pos(fp, rl, l), gl);
+        src = light_sample(fp, rl, l, gl, S);
         const V3 o = mk(ro), d = mk(rd);
         hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
         sd = sub(hit, src);                 // :920
@@ -710,7 +717,7 @@ __global__ void __launch_bounds__(128, 8) k_shade(const DevScene sc, const Frame
             const bool v = fp.point_light ? (vis[l] != 0) : (vis[Lmax + l * S + s] != 0);
             if (!v) continue;
             sum += 1.f;
-            const V3 spos = fp.point_light ? lpos : area_sample(fp, lpos, s);
+            const V3 spos = fp.point_light ? lpos : light_sample(fp, rl, l, s, S);
             acc = add(acc, phong_sample(Ikd, Iks, m.ns, hit, spos, normal, eye));
             samples_shaded++;
           }
