@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FramePa
   unsigned traced = 0;
   // jobs_per_slot == J: gate and sample rays of every hit; jobs_per_slot == Lmax: gate rays only (the
   // sample rays are then traced as packets by k_shadow_packet)
-  const unsigned n_jobs = (unsigned)fc->n_hits[level] * (unsigned)jobs_per_slot;
+  const int n_hits_level = fc->n_hits[level];
+  const unsigned n_jobs = (unsigned)n_hits_level * (unsigned)jobs_per_slot;
   unsigned long long *cursor = &fc->work_k2[level];
   RT_POOL_BATCH = pool_batch((unsigned long long)n_jobs);
 
@@ -331,8 +332,12 @@ __global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FramePa
       pool_next += (unsigned long long)__popc(idle);
       if (!active) {
         if (g64 < pool_end) {
-          const unsigned slot = (unsigned)g64 / (unsigned)jobs_per_slot;
-          const int j = (int)((unsigned)g64 - slot * (unsigned)jobs_per_slot);
+          // job order: sample-major.  Consecutive jobs are the SAME light sample towards consecutive hit
+          // slots (hits of one 8x4 pixel tile are adjacent in hit_list): a pinhole bundle from the sample
+          // to a small surface patch, far more coherent than the S rays that fan out from one hit point.
+          const unsigned n_slots = (unsigned)n_hits_level;
+          const int j = (int)((unsigned)g64 / n_slots);
+          const unsigned slot = (unsigned)g64 - (unsigned)j * n_slots;
           const unsigned g = slot * (unsigned)J + (unsigned)j;  // index into vis
           const int i = lv.hit_list[slot];
           const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
