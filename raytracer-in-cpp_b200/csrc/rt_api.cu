@@ -1163,26 +1163,36 @@ extern "C" int rt_write_ppm(const char *path, const uint8_t *rgba, int32_t width
       fwrite(row.data(), 1, row.size(), f);
     }
   } else {
-    // "r g b " per pixel, newline per row, exactly the reference's text layout
-    static const char digits[] = "0123456789";
-    fprintf(f, "P3\n%d %d\n255\n", width, height);
-    std::string line;
-    line.reserve((size_t)width * 12 + 2);
-    for (int j = 0; j < height; ++j) {
-      line.clear();
-      for (int i = 0; i < width; ++i) {
-        const uint8_t *px = rgba + ((size_t)j * width + i) * 4;
-        for (int c = 0; c < 3; ++c) {
-          const unsigned v = px[c];
-          if (v >= 100) line.push_back(digits[v / 100]);
-          if (v >= 10) line.push_back(digits[(v / 10) % 10]);
-          line.push_back(digits[v % 10]);
-          line.push_back(' ');
-        }
-      }
-      line.push_back('\n');
-      fwrite(line.data(), 1, line.size(), f);
+    // "r g b " per pixel, newline per row, exactly the reference's text layout.  Every value 0..255
+    // is pre-formatted once ("123 "), a pixel is three table copies; rows go out in 4 MiB chunks.
+    char tab[256][4];
+    uint8_t len[256];
+    for (int v = 0; v < 256; ++v) {
+      int n = 0;
+      if (v >= 100) tab[v][n++] = (char)('0' + v / 100);
+      if (v >= 10) tab[v][n++] = (char)('0' + (v / 10) % 10);
+      tab[v][n++] = (char)('0' + v % 10);
+      tab[v][n++] = ' ';
+      len[v] = (uint8_t)n;
     }
+    fprintf(f, "P3\n%d %d\n255\n", width, height);
+    std::vector<char> buf((size_t)4 << 20);
+    const size_t row_max = (size_t)width * 12 + 1;
+    if (buf.size() < row_max) buf.resize(row_max);
+    size_t used = 0;
+    for (int j = 0; j < height; ++j) {
+      if (used + row_max > buf.size()) { fwrite(buf.data(), 1, used, f); used = 0; }
+      char *o = buf.data() + used;
+      const uint8_t *px = rgba + (size_t)j * width * 4;
+      for (int i = 0; i < width; ++i, px += 4) {
+        memcpy(o, tab[px[0]], 4); o += len[px[0]];
+        memcpy(o, tab[px[1]], 4); o += len[px[1]];
+        memcpy(o, tab[px[2]], 4); o += len[px[2]];
+      }
+      *o++ = '\n';
+      used = (size_t)(o - buf.data());
+    }
+    fwrite(buf.data(), 1, used, f);
   }
   fclose(f);
   return RT_OK;

@@ -81,3 +81,55 @@ def test_full_frame_matches_oracle(case, pkg, capi, oracle_mod, scene_dir):
     assert (err <= 1).mean() >= 0.999, f"max err {err.max()}"
     print(f"{case}: full frame {len(px)} px, rgb8 exact {(err == 0).mean():.6f}, max err {int(err.max())}")
     scene.close()
+
+
+def test_known_answers_of_the_default_scene_on_gpu(pkg, capi):
+    """SURVEY.md section 4 known answers of the reference's own 1000x1000 cube render (point and area
+    light), reproduced by the CUDA path: background count, bounding box, pixel values, colour count, mean."""
+    g = load_golden("cube_point_1000")
+    capi.init(0)
+    scene = capi.Scene(g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    cam = capi.default_camera(1000, 1000)
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    fr = scene.render(cam, lights, capi.make_params(1000, 1000, 0, 1, -1))
+    img = fr.rgba[..., :3].astype(np.int64)
+    bg = (img == 255).all(-1)
+    assert int(bg.sum()) == 505791
+    nb = np.argwhere(~bg)
+    assert tuple(nb.min(0)) == (149, 149) and tuple(nb.max(0)) == (851, 851)
+    assert tuple(img[500, 500]) == (223, 223, 216) and tuple(img[250, 400]) == (255, 255, 216) and tuple(img[160, 160]) == (236, 236, 216)
+    assert len(np.unique(img.reshape(-1, 3), axis=0)) == 41
+    assert np.allclose(img.reshape(-1, 3).mean(0), (239.143, 239.143, 235.726), atol=2e-3)
+    assert set(np.unique(fr.face)) == {-1, 10, 11}
+    # ray census of App. A.8: 494 209 hit pixels x (1 primary + 1 merged gate/sample ray + 1 child) + misses
+    assert fr.stats["rays_primary"] == 1000000 and fr.stats["rays_shadow"] == 494209 and fr.stats["rays_secondary"] == 494209
+    fa = scene.render(cam, lights, capi.make_params(1000, 1000, 1, 0, -1))
+    ia = fa.rgba[..., :3].astype(np.int64)
+    assert tuple(ia[500, 500]) == (232, 232, 216) and tuple(ia[250, 400]) == (239, 239, 216) and tuple(ia[160, 160]) == (220, 220, 216)
+    assert np.allclose(ia.reshape(-1, 3).mean(0), (239.273, 239.273, 235.726), atol=2e-3)
+    # (1 gate + 25 samples) per hit; the mirror children leave the convex cube and hit nothing (App. A.8: x28)
+    assert fa.stats["rays_shadow"] == 494209 * 26 and fa.stats["rays_secondary"] == 494209
+
+
+def test_headline_config_full_frame_vs_oracle(pkg, capi, oracle_mod):
+    """BASELINE configs[1] exactly as bench.py runs it (cube, 1920x1080, 4x4 area light, depth 3):
+    every one of the 2 073 600 pixels against the oracle."""
+    O = oracle_mod
+    g = load_golden("cube_point_1000")
+    arrs = (g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    capi.init(0)
+    scene = capi.Scene(*arrs)
+    W, H = 1920, 1080
+    lights_np = np.array([[-1, 1, 1]], np.float32)
+    fr = scene.render(capi.default_camera(W, H), capi.Lights(lights_np), capi.make_params(W, H, 1, 0, 3, (4, 4)))
+    orc = O.Oracle(O.BakedScene(*arrs), area=1, point=0, max_depth=3, grid=(4, 4))
+    cam = O.Oracle.camera((0, 0, 2), np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2]], np.float32), (0, 0, W, H), 60.0,
+                          np.float32(W) / np.float32(H))
+    pxy, rgb, face, t, rgb8 = orc.render(cam, lights_np, W, H, stride=1, threads=16)
+    px, py = pxy[:, 0], pxy[:, 1]
+    assert (fr.face[py, px] == face).all()
+    assert (fr.t[py, px].view(np.uint32) == t.view(np.uint32)).all()
+    err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - quant(rgb)).max(-1)
+    same_f32 = (fr.rgb[py, px].view(np.uint32) == rgb.view(np.uint32)).all(-1).mean()
+    print(f"C2 full frame: {len(px)} px, rgb8 exact {(err == 0).mean():.7f}, max err {int(err.max())}, float RGB bit-identical {same_f32:.7f}")
+    assert err.max() <= 1 and (err == 0).mean() >= 0.99999
