@@ -38,6 +38,7 @@ int g_opt_leaf = 2;  // measured best on the 100 k / 1 M-triangle scenes (leaf t
 int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
 int g_opt_ref_candidates = 1;
 int g_opt_shadow_packets = 0;  // 1/2: area-light sample rays traced as lockstep packets (measured slower)
+int g_opt_graph_cond = 1;  // skip empty bounce levels inside the frame graph (conditional nodes)
 int g_opt_refill_below = 0;  // dynamic fetch: refill a warp when fewer lanes than this still traverse (0 = when all are done)
 
 int fail(int code, const char *fmt, ...) {
@@ -189,6 +190,7 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
   else if (!strcmp(key, "reference_candidates")) g_opt_ref_candidates = value ? 1 : 0;
   else if (!strcmp(key, "refill_below")) g_opt_refill_below = std::max(0, std::min(32, value));
+  else if (!strcmp(key, "graph_conditionals")) g_opt_graph_cond = value ? 1 : 0;
   else if (!strcmp(key, "shadow_packets")) g_opt_shadow_packets = std::max(0, std::min(2, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
@@ -700,7 +702,7 @@ int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *
       else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
     }
     launch_shadow(sc, pl, fpp, lv, level, fc, st, pl.trav_stats ? grid_k2_s : grid_k2, launches);
-    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc);
+    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc, 0);
     *launches += 2;
   }
   for (int level = pl.depth_cap - 1; level >= 0; --level) {
@@ -710,6 +712,113 @@ int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *
   }
   CUDA_TRY(cudaGetLastError());
   return RT_OK;
+}
+
+// Frame graph with conditional nodes: the kernels of bounce level k+1 (and, nested inside, everything
+// deeper, and the fold of level k) sit in the body of an IF node whose condition K3 of level k sets to
+// "some ray was spawned".  A depth cap above the scene's natural depth then costs nothing: on the
+// cube scene (natural depth 1, cap 3) a frame is 7 kernel launches instead of 15.
+//   root : memset, K1_0, K2_0, K3_0, IF(h1){ body_1 }
+//   body_k: K1_k, K2_k, K3_k, IF(h_{k+1}){ body_{k+1} }, fold_{k-1}
+// Built by capturing the launches of each level into its (body) graph and splicing the explicit
+// conditional node into the capture.  Any failure returns an error and the caller falls back to the
+// plain captured graph.
+int enqueue_level(RtScene *sc, const FramePlan &pl, cudaStream_t cs, int level, cudaGraphConditionalHandle next_cond) {
+  const FrameParams *fpp = sc->frame_params.as<FrameParams>();
+  FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
+  static int g1p = 0, g1s = 0, g2 = 0, g1ps = 0, g1ss = 0, g2s = 0;
+  if (!g1p) {
+    g1p = persistent_grid(k_trace_nearest<true, false>, 128); g1s = persistent_grid(k_trace_nearest<false, false>, 128);
+    g2 = persistent_grid(k_shadow<false>, 128); g1ps = persistent_grid(k_trace_nearest<true, true>, 128);
+    g1ss = persistent_grid(k_trace_nearest<false, true>, 128); g2s = persistent_grid(k_shadow<true>, 128);
+  }
+  const int elem_blocks = std::max(1, std::min((pl.n0 + 127) / 128, g_sm_count * 16));
+  LevelBufs lv = sc->levels[level].bufs();
+  LevelBufs nx = sc->levels[level + 1].bufs();
+  const int n_param = level == 0 ? pl.n0 : -1;
+  int launches = 0;
+  if (level == 0 && !pl.explicit_rays) {
+    if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+    else k_trace_nearest<true, false><<<g1p, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+  } else {
+    if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+    else k_trace_nearest<false, false><<<g1s, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+  }
+  launch_shadow(sc, pl, fpp, lv, level, fc, cs, pl.trav_stats ? g2s : g2, &launches);
+  k_shade<<<elem_blocks, 128, 0, cs>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc, next_cond);
+  CUDA_TRY(cudaGetLastError());
+  return RT_OK;
+}
+
+// An IF node costs about as much as three empty launches (~10 us measured), so level 1 -- non-empty in
+// any scene with a reflective or transparent surface -- stays unconditional in the root graph and the
+// conditionals start at level 2:
+//   root  : memset, K1_0, K2_0, K3_0, K1_1, K2_1, K3_1, IF(h2){ body_2 }, fold_0
+//   body_k: K1_k, K2_k, K3_k, IF(h_{k+1}){ body_{k+1} }, fold_{k-1}          (k >= 2)
+constexpr int kFirstConditionalLevel = 2;
+
+int build_level_graph(RtScene *sc, const FramePlan &pl, cudaStream_t cs, cudaGraph_t graph, int first_level) {
+  const FrameParams *fpp = sc->frame_params.as<FrameParams>();
+  FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
+  const int elem_blocks = std::max(1, std::min((pl.n0 + 127) / 128, g_sm_count * 16));
+  // levels captured straight into this graph: the root takes 0 .. kFirstConditionalLevel-1, a body takes one
+  const int last_level = first_level == 0 ? std::min(pl.depth_cap, kFirstConditionalLevel - 1) : first_level;
+  const bool has_next = last_level < pl.depth_cap;
+  cudaGraphConditionalHandle h_next = 0;
+  if (has_next) CUDA_TRY(cudaGraphConditionalHandleCreate(&h_next, graph, 0, cudaGraphCondAssignDefault));
+  CUDA_TRY(cudaStreamBeginCaptureToGraph(cs, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  int rc = RT_OK;
+  cudaGraph_t body = nullptr;
+  do {
+    if (first_level == 0) {
+      cudaError_t e = cudaMemsetAsync(fc, 0, sizeof(FrameCounts), cs);
+      if (e != cudaSuccess) { rc = fail(RT_ERR_CUDA, "memset node: %s", cudaGetErrorString(e)); break; }
+    }
+    for (int level = first_level; level <= last_level && rc == RT_OK; ++level)
+      rc = enqueue_level(sc, pl, cs, level, level == last_level ? h_next : 0);
+    if (rc) break;
+    if (has_next) {
+      cudaStreamCaptureStatus status;
+      const cudaGraphNode_t *deps = nullptr;
+      size_t ndeps = 0;
+      cudaError_t e = cudaStreamGetCaptureInfo_v2(cs, &status, nullptr, nullptr, &deps, &ndeps);
+      if (e != cudaSuccess) { rc = fail(RT_ERR_CUDA, "cudaStreamGetCaptureInfo: %s", cudaGetErrorString(e)); break; }
+      cudaGraphNodeParams cp = {};
+      cp.type = cudaGraphNodeTypeConditional;
+      cp.conditional.handle = h_next;
+      cp.conditional.type = cudaGraphCondTypeIf;
+      cp.conditional.size = 1;
+      cudaGraphNode_t cnode;
+      e = cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp);
+      if (e != cudaSuccess) { rc = fail(RT_ERR_CUDA, "conditional node: %s", cudaGetErrorString(e)); break; }
+      body = cp.conditional.phGraph_out[0];
+      e = cudaStreamUpdateCaptureDependencies(cs, &cnode, 1, cudaStreamSetCaptureDependencies);
+      if (e != cudaSuccess) { rc = fail(RT_ERR_CUDA, "cudaStreamUpdateCaptureDependencies: %s", cudaGetErrorString(e)); break; }
+    }
+    // folds owned by this graph, deepest first: a body folds the level above it, the root folds 0 .. last_level-1
+    const int fold_hi = first_level == 0 ? last_level - 1 : first_level - 1;
+    const int fold_lo = first_level == 0 ? 0 : first_level - 1;
+    for (int k = fold_hi; k >= fold_lo; --k)
+      k_fold<<<elem_blocks, 256, 0, cs>>>(fpp, sc->levels[k].bufs(), sc->levels[k + 1].bufs(), k, k == 0 ? pl.n0 : -1, fc);
+  } while (false);
+  cudaGraph_t same = nullptr;
+  cudaError_t e = cudaStreamEndCapture(cs, &same);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaStreamEndCapture (level %d): %s", first_level, cudaGetErrorString(e));
+  if (has_next) return build_level_graph(sc, pl, cs, body, last_level + 1);
+  return RT_OK;
+}
+
+int build_conditional_frame_graph(RtScene *sc, const FramePlan &pl, cudaGraphExec_t *exec_out) {
+  cudaGraph_t graph = nullptr;
+  CUDA_TRY(cudaGraphCreate(&graph, 0));
+  int rc = build_level_graph(sc, pl, sc->stream, graph, 0);
+  if (rc == RT_OK) {
+    cudaError_t e = cudaGraphInstantiate(exec_out, graph, 0);
+    if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "cudaGraphInstantiate (conditional): %s", cudaGetErrorString(e));
+  }
+  cudaGraphDestroy(graph);
+  return rc;
 }
 
 int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int n0, uchar4 *d_rgba, int32_t *d_face,
@@ -755,10 +864,16 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
     for (int l = 0; l <= pl.depth_cap; ++l)
       if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
-    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.refill, pl.packet_group,
+    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.refill, pl.packet_group, g_opt_graph_cond,
                                         (long long)pl.explicit_rays, (long long)pl.trav_stats};
     if (sc->graph_exec == nullptr || key != sc->graph_key) {
       if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
+      if (g_opt_graph_cond && pl.depth_cap >= kFirstConditionalLevel) {
+        if (build_conditional_frame_graph(sc, pl, &sc->graph_exec) == RT_OK) sc->graph_key = key;
+        else { cudaGetLastError(); sc->graph_exec = nullptr; }  // fall back to the plain captured graph below
+      }
+    }
+    if (sc->graph_exec == nullptr || key != sc->graph_key) {
       cudaGraph_t graph = nullptr;
       CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       rc = enqueue_frame_async(sc, pl, st, &launches);
@@ -816,7 +931,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     }
     LevelBufs nx = sc->levels[std::min(level + 1, (int)sc->levels.size() - 1)].bufs();
     timer.begin(2);
-    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc);
+    k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc, 0);
     timer.end();
     launches += 2;
     levels_run = level + 1;

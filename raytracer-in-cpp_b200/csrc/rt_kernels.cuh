@@ -61,6 +61,7 @@ struct FrameCounts {
   unsigned long long work_k2p[RT_MAX_LEVELS];  // packet shadow kernel
   int32_t n_rays[RT_MAX_LEVELS];              // rays queued at level k (k >= 1; level 0 comes as a parameter)
   int32_t n_hits[RT_MAX_LEVELS];              // rays of level k that hit a primitive
+  uint32_t k3_done[RT_MAX_LEVELS];            // CTAs of K3(level k) that have finished (last one sets the graph condition)
   Counters ctr;
 };
 
@@ -673,7 +674,8 @@ __device__ __forceinline__ V3 phong_sample(V3 Ikd, V3 Iks, float shininess, V3 h
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 8) k_shade(const DevScene sc, const FrameParams *__restrict__ fpp,
                                               const LevelBufs lv, const LevelBufs nx, const int level, const int J,
-                                              const int Lmax, const int S, FrameCounts *fc) {
+                                              const int Lmax, const int S, FrameCounts *fc,
+                                              const cudaGraphConditionalHandle next_level_cond) {
   RT_STAGE_FRAME_PARAMS(fpp);
   uchar4 *fb = level == 0 ? fp.out_rgba : nullptr;
   float *rgb_f32 = level == 0 ? fp.out_rgbf : nullptr;
@@ -774,6 +776,20 @@ __global__ void __launch_bounds__(128, 8) k_shade(const DevScene sc, const Frame
   }
   for (int off = 16; off > 0; off >>= 1) samples_shaded += __shfl_down_sync(0xffffffffu, samples_shaded, off);
   if ((threadIdx.x & 31) == 0 && samples_shaded) atomicAdd(&fc->ctr.shade_samples, (unsigned long long)samples_shaded);
+  // CUDA-graph replay: the last CTA to finish tells the graph whether the next bounce level has any
+  // rays; if not, the conditional node that holds that level's kernels (and everything deeper) is skipped
+  if (next_level_cond != 0) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(&fc->k3_done[level], 1u);
+      if (prev == gridDim.x - 1) {
+        __threadfence();
+        const int spawned = atomicAdd(&fc->n_rays[level + 1], 0);
+        cudaGraphSetConditional(next_level_cond, spawned > 0 ? 1u : 0u);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
