@@ -13,7 +13,8 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librt_b200.so")
+# RT_B200_LIB: developer override for A/B runs of two builds of the same C ABI
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")
 
 RT_MAX_LIGHTS = 25
 
