@@ -134,9 +134,7 @@ int rt_device_name(char *buf, size_t n);
 /* runtime knobs: "stats" (0/1 traversal counters), "leaf_size", "persistent_ctas_per_sm",
  * "reference_candidates" (default 1: scenes created afterwards filter BVH hits through the
  * reference's octree candidate sets so that the image matches the reference bit for bit; 0: plain
- * BVH = exact nearest hit over all faces), "refill_below" (dynamic ray fetch: persistent warps hand new
- * rays to their idle lanes once fewer than this many lanes are still traversing; 0 = only when all
- * 32 are done), "shadow_packets" (0, default: every shadow ray is traced on its own; 1: the
+ * BVH = exact nearest hit over all faces), "shadow_packets" (0, default: every shadow ray is traced on its own; 1: the
  * area-light sample rays of a hit are traced as lockstep packets when the BVH has >= 64 nodes; 2: always),
  * "graph_conditionals" (1, default: empty bounce levels are skipped inside the frame's CUDA graph) */
 int rt_set_option(const char *key, int value);

@@ -39,7 +39,6 @@ int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
 int g_opt_ref_candidates = 1;
 int g_opt_shadow_packets = 0;  // 1/2: area-light sample rays traced as lockstep packets (measured slower)
 int g_opt_graph_cond = 1;  // skip empty bounce levels inside the frame graph (conditional nodes)
-int g_opt_refill_below = 0;  // dynamic fetch: refill a warp when fewer lanes than this still traverse (0 = when all are done)
 
 int fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -85,7 +84,7 @@ struct DevBuf {
 };
 
 struct LevelStore {
-  DevBuf ray_o, ray_d, ray_l, hit_t, hit_face, hit_list, vis, rec, child, type;
+  DevBuf ray_o, ray_d, ray_l, hit_t, hit_face, hit_list, hit_p, vis, rec, child, type;
   int reserve(size_t n, size_t J) {
     n = std::max<size_t>(n, 1);
     int rc;
@@ -95,6 +94,7 @@ struct LevelStore {
     if ((rc = hit_t.reserve(n * 4))) return rc;
     if ((rc = hit_face.reserve(n * 4))) return rc;
     if ((rc = hit_list.reserve(n * 4))) return rc;
+    if ((rc = hit_p.reserve(n * 16))) return rc;
     if ((rc = vis.reserve(n * std::max<size_t>(J, 1)))) return rc;
     if ((rc = rec.reserve(n * 16))) return rc;
     if ((rc = child.reserve(n * 4))) return rc;
@@ -105,12 +105,13 @@ struct LevelStore {
     LevelBufs b;
     b.ray_o = ray_o.as<float4>(); b.ray_d = ray_d.as<float4>(); b.ray_l = ray_l.as<float2>();
     b.hit_t = hit_t.as<float>(); b.hit_face = hit_face.as<int32_t>(); b.hit_list = hit_list.as<int32_t>();
+    b.hit_p = hit_p.as<float4>();
     b.vis = vis.as<uint8_t>();
     b.rec = rec.as<float4>(); b.child = child.as<int32_t>(); b.type = type.as<uint8_t>();
     return b;
   }
   void release() {
-    ray_o.release(); ray_d.release(); ray_l.release(); hit_t.release(); hit_face.release(); hit_list.release();
+    ray_o.release(); ray_d.release(); ray_l.release(); hit_t.release(); hit_face.release(); hit_list.release(); hit_p.release();
     vis.release(); rec.release(); child.release(); type.release();
   }
 };
@@ -189,7 +190,6 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "leaf_size")) g_opt_leaf = std::max(1, std::min(16, value));
   else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
   else if (!strcmp(key, "reference_candidates")) g_opt_ref_candidates = value ? 1 : 0;
-  else if (!strcmp(key, "refill_below")) g_opt_refill_below = std::max(0, std::min(32, value));
   else if (!strcmp(key, "graph_conditionals")) g_opt_graph_cond = value ? 1 : 0;
   else if (!strcmp(key, "shadow_packets")) g_opt_shadow_packets = std::max(0, std::min(2, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
@@ -657,7 +657,7 @@ constexpr int kAsyncDepth = 8;
 
 struct FramePlan {
   bool explicit_rays, trav_stats, async;
-  int n0, J, Lmax, S, depth_cap, refill;
+  int n0, J, Lmax, S, depth_cap;
   int packet_group;  // 0: every shadow ray through k_shadow; 16 / 32: sample rays as packets of that many lanes
 };
 
@@ -665,8 +665,8 @@ struct FramePlan {
 void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, const LevelBufs &lv, int level, FrameCounts *fc,
                    cudaStream_t st, int grid, int *launches) {
   const int jobs = pl.packet_group ? pl.Lmax : pl.J;
-  if (pl.trav_stats) k_shadow<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc, pl.refill);
-  else k_shadow<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc, pl.refill);
+  if (pl.trav_stats) k_shadow<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc);
+  else k_shadow<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc);
   *launches += 1;
   if (pl.packet_group) {
     if (pl.trav_stats) k_shadow_packet<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, pl.packet_group, fc);
@@ -695,11 +695,11 @@ int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *
     LevelBufs nx = sc->levels[level + 1].bufs();
     const int n_param = level == 0 ? pl.n0 : -1;
     if (level == 0 && !pl.explicit_rays) {
-      if (pl.trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
-      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      if (pl.trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
+      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
     } else {
-      if (pl.trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
-      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      if (pl.trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
+      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
     }
     launch_shadow(sc, pl, fpp, lv, level, fc, st, pl.trav_stats ? grid_k2_s : grid_k2, launches);
     k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc, 0);
@@ -738,11 +738,11 @@ int enqueue_level(RtScene *sc, const FramePlan &pl, cudaStream_t cs, int level, 
   const int n_param = level == 0 ? pl.n0 : -1;
   int launches = 0;
   if (level == 0 && !pl.explicit_rays) {
-    if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
-    else k_trace_nearest<true, false><<<g1p, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+    if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
+    else k_trace_nearest<true, false><<<g1p, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
   } else {
-    if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
-    else k_trace_nearest<false, false><<<g1s, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+    if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
+    else k_trace_nearest<false, false><<<g1s, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
   }
   launch_shadow(sc, pl, fpp, lv, level, fc, cs, pl.trav_stats ? g2s : g2, &launches);
   k_shade<<<elem_blocks, 128, 0, cs>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc, next_cond);
@@ -839,7 +839,6 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
   pl.Lmax = std::max(1, fp.n_lights);
   pl.S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
   pl.J = pl.Lmax + pl.Lmax * pl.S;
-  pl.refill = g_opt_refill_below;
   // packets pay off when rays actually walk a tree; on a handful of nodes the per-ray kernel is already converged
   pl.packet_group = 0;
   if (g_opt_shadow_packets && pl.S >= 4 && (sc->dev.n_nodes >= 64 || g_opt_shadow_packets == 2)) pl.packet_group = pl.S <= 16 ? 16 : 32;
@@ -864,7 +863,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
     for (int l = 0; l <= pl.depth_cap; ++l)
       if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
-    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.refill, pl.packet_group, g_opt_graph_cond,
+    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.packet_group, g_opt_graph_cond,
                                         (long long)pl.explicit_rays, (long long)pl.trav_stats};
     if (sc->graph_exec == nullptr || key != sc->graph_key) {
       if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
@@ -914,11 +913,11 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     const int n_param = level == 0 ? n0 : -1;
     timer.begin(0);
     if (level == 0 && !explicit_rays) {
-      if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
-      else k_trace_nearest<true, false><<<g1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
+      else k_trace_nearest<true, false><<<g1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
     } else {
-      if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
-      else k_trace_nearest<false, false><<<g1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc, pl.refill);
+      if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
+      else k_trace_nearest<false, false><<<g1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
     }
     timer.end();
     timer.begin(1);

@@ -36,6 +36,7 @@ struct LevelBufs {
   float *hit_t;
   int32_t *hit_face;  // -1: no hit
   int32_t *hit_list;  // compacted indices of the rays that hit something (K1 -> K2, K3)
+  float4 *hit_p;      // per hit slot: (hit point, bits((ray index << 1) | single-light flag)) (K1 -> K2)
   uint8_t *vis;       // [hit slot][J] visibility of every shadow job
   float4 *rec;        // (P or colour, fresnel factor)
   int32_t *child;     // slot of the child ray in the next level, -1 if none
@@ -87,8 +88,6 @@ __device__ __forceinline__ size_t fb_index(const FrameParams &fp, int i) {
 // level-0 pixel written); rays that hit are compacted into hit_list with one atomic per warp.
 // n0 >= 0: item count given by the host (level 0); n0 < 0: read fc->n_rays[level].
 // ---------------------------------------------------------------------------------------------
-// Lanes of a persistent warp are refilled with new rays as soon as fewer than this many are still
-// traversing (dynamic fetch); the traversal of the remaining lanes resumes where it stopped.
 // Work items a warp takes from the global cursor per atomic.  Small when the launch has little work
 // (so that every resident warp gets some), up to 96 when there is plenty (atomic off the critical path).
 __device__ __forceinline__ unsigned long long pool_batch(unsigned long long n_items) {
@@ -98,146 +97,122 @@ __device__ __forceinline__ unsigned long long pool_batch(unsigned long long n_it
 }
 
 template <bool PRIMARY, bool STATS>
-__global__ void __launch_bounds__(128) k_trace_nearest(const DevScene sc, const FrameParams *__restrict__ fpp,
+__global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, const FrameParams *__restrict__ fpp,
                                                       const LevelBufs lv, const int level, const int n0,
-                                                      FrameCounts *fc, const int refill_below) {
+                                                      FrameCounts *fc) {
   RT_STAGE_FRAME_PARAMS(fpp);
   int32_t *face_out = level == 0 ? fp.out_face : nullptr;
   float *t_out = level == 0 ? fp.out_t : nullptr;
   uchar4 *fb = level == 0 ? fp.out_rgba : nullptr;
   float *rgb_f32 = level == 0 ? fp.out_rgbf : nullptr;
   const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of work items (warp-uniform)
-  unsigned long long RT_POOL_BATCH = 32ull;
   TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   const int tiles_x = PRIMARY ? (fp.width + 7) >> 3 : 1;
   const int n = n0 >= 0 ? n0 : fc->n_rays[level];
-  const long long n_items = PRIMARY ? (long long)tiles_x * ((fp.local_rows + 3) >> 2) * 32 : n;
+  const unsigned long long n_items =
+      PRIMARY ? (unsigned long long)tiles_x * (unsigned long long)((fp.local_rows + 3) >> 2) * 32ull : (unsigned long long)n;
   unsigned long long *cursor = &fc->work_k1[level];
-  RT_POOL_BATCH = pool_batch((unsigned long long)n_items);
+  const unsigned long long batch = pool_batch(n_items);
+  unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of work items (warp-uniform)
 
   Trav<false, STATS> tr;
   int stack[RT_STACK_SIZE];
-  bool active = false;     // this lane holds a ray that is still being traversed
-  bool retire = false;     // this lane finished a ray in the previous round; results not yet written
-  bool exhausted = false;  // the work cursor ran past the end (warp-uniform)
-  int cur_i = 0;           // ray / local pixel index of the lane's ray
-  float fin_t = RT_NO_HIT_T;
-  int fin_id = -1;
+  tr.idle();
 
   for (;;) {
-    // ---- retire finished rays (all 32 lanes converge here: one hit-list atomic per warp) ----
-    {
-      const bool hit = retire && fin_id >= 0;
-      const int slot = warp_append(&fc->n_hits[level], hit);
-      if (retire) {
-        const int i = cur_i;
-        if (hit) {
-          if (PRIMARY) {
-            lv.ray_o[i] = make_float4(tr.o.x, tr.o.y, tr.o.z, __int_as_float(0));
-            lv.ray_d[i] = make_float4(tr.d.x, tr.d.y, tr.d.z, 0.f);
-          }
-          lv.hit_t[i] = fin_t;
-          lv.hit_face[i] = fin_id;
-          lv.hit_list[slot] = i;
-        } else {
-          // BACKGROUND, src/flyscene.cpp:658-665 / :684-691
-          lv.rec[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-          lv.type[i] = (uint8_t)REC_TERMINAL;
-          if (level == 0) {
-            if (fb) fb[fb_index(fp, i)] = make_uchar4(255, 255, 255, 255);
-            if (rgb_f32) { rgb_f32[3 * (size_t)i] = 1.f; rgb_f32[3 * (size_t)i + 1] = 1.f; rgb_f32[3 * (size_t)i + 2] = 1.f; }
-          }
+    if (pool_next >= pool_end) {
+      // one global atomic per `batch` items; the warp then walks the batch 32 items at a time
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(cursor, batch);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= n_items) break;
+      pool_next = base;
+      pool_end = base + batch < n_items ? base + batch : n_items;
+    }
+    const unsigned long long item = pool_next + (unsigned long long)lane;
+    pool_next += 32ull;
+    int i = 0, single = 0;
+    bool valid = false, active = false;
+    float fin_t = RT_NO_HIT_T;
+    int fin_id = -1;
+    if (item < pool_end) {
+      V3 o, d;
+      V3 screen = mk(0.f, 0.f, 0.f);
+      bool tri_enabled = true;
+      if constexpr (PRIMARY) {
+        const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int px = tx * 8 + (in_tile & 7), py = ty * 4 + (in_tile >> 3);
+        valid = px < fp.width && py < fp.local_rows;
+        i = py * fp.width + px;
+        o = ld3(fp.eye);
+        d = mk(0.f, 0.f, 0.f);
+        if (valid) {
+          screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
+          d = sub(screen, o);  // :619, not normalised
         }
+      } else {
+        i = (int)item;
+        valid = true;
+        const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
+        o = mk(ro); d = mk(rd);
+        single = __float_as_int(ro.w) & 1;
+      }
+      if (valid) {
+        // one exact reciprocal of the direction serves both root-box tests and the traversal
+        const V3 rdir = recip_dir(d);
+        if constexpr (PRIMARY) {
+          // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
+          // (scenes with analytic spheres -- not a reference feature -- skip it, like rt_oracle.c)
+          tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || sc.n_spheres > 0;
+        }
+        // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
+        const V3 dest = add(o, d);
+        tri_enabled = tri_enabled && ref_box_intersect_quick(sc.root_min, sc.root_max, o, dest, rdir);
+        if (tri_enabled || sc.n_spheres > 0) {  // else: missed the root box, BACKGROUND
+          tr.init(o, d, dest, tri_enabled, rdir);
+          active = true;
+        }
+      }
+    }
+    // ---- traverse: the whole warp, lanes without a ray idle inside run() ----
+    for (;;) {
+      tr.run(sc, st, stack, 0xffffffffu);
+      if (active && tr.finish(sc, st)) {
+        active = false;
+        fin_t = tr.best_t;
+        fin_id = tr.best_id;
+      }
+      if (!__any_sync(0xffffffffu, active)) break;
+    }
+    // ---- retire (all 32 lanes converge here: one hit-list atomic per warp) ----
+    const bool hit = valid && fin_id >= 0;
+    const int slot = warp_append(&fc->n_hits[level], hit);
+    if (valid) {
+      if (hit) {
+        if (PRIMARY) {
+          lv.ray_o[i] = make_float4(tr.o.x, tr.o.y, tr.o.z, __int_as_float(0));
+          lv.ray_d[i] = make_float4(tr.d.x, tr.d.y, tr.d.z, 0.f);
+        }
+        lv.hit_t[i] = fin_t;
+        lv.hit_face[i] = fin_id;
+        lv.hit_list[slot] = i;
+        const V3 hit = add(tr.o, mul(fin_t, tr.d));  // src/flyscene.cpp:695
+        lv.hit_p[slot] = make_float4(hit.x, hit.y, hit.z, __int_as_float((i << 1) | single));
+      } else {
+        // BACKGROUND, src/flyscene.cpp:658-665 / :684-691
+        lv.rec[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        lv.type[i] = (uint8_t)REC_TERMINAL;
         if (level == 0) {
-          if (face_out) face_out[i] = fin_id;
-          if (t_out) t_out[i] = fin_t;
-        }
-        retire = false;
-      }
-    }
-    // ---- refill idle lanes ----
-    const unsigned idle = __ballot_sync(0xffffffffu, !active);
-    if (idle != 0u && !(exhausted && pool_next >= pool_end)) {
-      if (pool_next >= pool_end && !exhausted) {
-        // one global atomic per RT_POOL_BATCH items; lanes are then refilled from the warp-local pool
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, RT_POOL_BATCH);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        pool_next = base;
-        pool_end = base + RT_POOL_BATCH < (unsigned long long)n_items ? base + RT_POOL_BATCH : (unsigned long long)n_items;
-        if (base >= (unsigned long long)n_items) { exhausted = true; pool_end = pool_next; }
-      }
-      const unsigned long long my_item = pool_next + (unsigned long long)__popc(idle & lt_mask);
-      pool_next += (unsigned long long)__popc(idle);
-      if (!active) {
-        const long long item = (long long)my_item;
-        if (my_item < pool_end) {
-          int i;
-          bool valid;
-          V3 o, d;
-          V3 screen = mk(0.f, 0.f, 0.f);
-          bool tri_enabled = true;
-          if constexpr (PRIMARY) {
-            const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
-            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int px = tx * 8 + (in_tile & 7), py = ty * 4 + (in_tile >> 3);
-            valid = px < fp.width && py < fp.local_rows;
-            i = py * fp.width + px;
-            o = ld3(fp.eye);
-            d = mk(0.f, 0.f, 0.f);
-            if (valid) {
-              screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
-              d = sub(screen, o);  // :619, not normalised
-            }
-          } else {
-            i = (int)item;
-            valid = true;
-            const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
-            o = mk(ro); d = mk(rd);
-          }
-          if (valid) {
-            // one exact reciprocal of the direction serves both root-box tests and the traversal
-            const V3 rdir = recip_dir(d);
-            if constexpr (PRIMARY) {
-              // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
-              // (scenes with analytic spheres -- not a reference feature -- skip it, like rt_oracle.c)
-              tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || sc.n_spheres > 0;
-            }
-            // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
-            const V3 dest = add(o, d);
-            tri_enabled = tri_enabled && ref_box_intersect_quick(sc.root_min, sc.root_max, o, dest, rdir);
-            cur_i = i;
-            tr.init(o, d, dest, tri_enabled, rdir);
-            if (tri_enabled || sc.n_spheres > 0) {
-              active = true;
-            } else {
-              retire = true; fin_t = RT_NO_HIT_T; fin_id = -1;  // missed the root box: BACKGROUND
-            }
-          }
+          if (fb) fb[fb_index(fp, i)] = make_uchar4(255, 255, 255, 255);
+          if (rgb_f32) { rgb_f32[3 * (size_t)i] = 1.f; rgb_f32[3 * (size_t)i + 1] = 1.f; rgb_f32[3 * (size_t)i + 2] = 1.f; }
         }
       }
-    }
-    const bool any_active = __any_sync(0xffffffffu, active);
-    const bool any_retire = __any_sync(0xffffffffu, retire);
-    if (!any_active) {
-      if (any_retire) continue;
-      if (exhausted && pool_next >= pool_end) break;
-      continue;
-    }
-    // ---- traverse (resumes where the lane stopped) ----
-    if (active) {
-      if (tr.run(sc, st, stack, (exhausted && pool_next >= pool_end) ? 1 : refill_below)) {
-        if (tr.finish(sc, st)) {
-          active = false;
-          retire = true;
-          fin_t = tr.best_t;
-          fin_id = tr.best_id;
-        }
+      if (level == 0) {
+        if (face_out) face_out[i] = fin_id;
+        if (t_out) t_out[i] = fin_t;
       }
     }
-    __syncwarp();
   }
   if (STATS) {
     atomicAdd(&fc->ctr.box_tests, (unsigned long long)st.box_tests);
@@ -286,109 +261,95 @@ __device__ __forceinline__ V3 light_sample(const FrameParams &fp, const RayLight
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: shadow rays for the rays of hit_list.  Job g = slot * J + j;  j < Lmax: gate ray towards light j
-// (:699);  j >= Lmax: sample ray (light (j-Lmax)/S, sample (j-Lmax)%S) of phongShade's lightStrikes
-// (:836).  In point mode the sample ray of a light IS its gate ray, so only the gate jobs exist.
+// K2: shadow rays for the rays of hit_list.  Job (slot, j) writes vis[slot * J + j]:
+//   j < Lmax : gate ray towards light j (lightStrikes of traceRay, src/flyscene.cpp:699);
+//   j >= Lmax: sample ray (light (j-Lmax)/S, sample (j-Lmax)%S) of phongShade's lightStrikes (:836).
+// In point mode the sample ray of a light IS its gate ray, so only the gate jobs exist (S = 0).
 // Rays are shot from the light sample towards the hit point, exactly like the reference
 // (origin = sample, direction = hit - sample, occluded iff some face has 1e-5 < t < 0.98).
-// Each warp takes 4 x 32 jobs per cursor update to keep the atomic off the critical path.
+// Work unit = one warp-round: job j for the 32 consecutive hit slots of one chunk; units are numbered
+// j-major (unit = j * n_chunks + chunk).  The 32 lanes of a round are hits of one 8x4 pixel tile
+// (hit_list order) looking at the SAME light sample: a pinhole bundle from the sample to a small
+// surface patch, far more coherent than the S rays that fan out from one hit point; and at any moment
+// all warps of the GPU work on the same one or two samples, which keeps the upper tree levels of that
+// bundle in L1.  j is warp-uniform, the per-job set-up is one 16-byte load of the hit point (hit_p).
+// jobs_per_slot == J: gate and sample rays of every hit; jobs_per_slot == Lmax: gate rays only (the
+// sample rays are then traced as packets by k_shadow_packet).
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_shadow(const DevScene sc, const FrameParams *__restrict__ fpp,
+__global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const FrameParams *__restrict__ fpp,
                                                const LevelBufs lv, const int level, const int J, const int Lmax,
-                                               const int S, const int jobs_per_slot, FrameCounts *fc,
-                                               const int refill_below) {
+                                               const int S, const int jobs_per_slot, FrameCounts *fc) {
   RT_STAGE_FRAME_PARAMS(fpp);
   const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of jobs (warp-uniform)
-  unsigned long long RT_POOL_BATCH = 32ull;
   TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   unsigned traced = 0;
-  // jobs_per_slot == J: gate and sample rays of every hit; jobs_per_slot == Lmax: gate rays only (the
-  // sample rays are then traced as packets by k_shadow_packet)
-  const int n_hits_level = fc->n_hits[level];
-  const unsigned n_jobs = (unsigned)n_hits_level * (unsigned)jobs_per_slot;
+  const unsigned n_slots = (unsigned)fc->n_hits[level];
+  const unsigned n_chunks = (n_slots + 31u) >> 5;
+  const unsigned long long n_units = (unsigned long long)n_chunks * (unsigned long long)jobs_per_slot;
   unsigned long long *cursor = &fc->work_k2[level];
-  RT_POOL_BATCH = pool_batch((unsigned long long)n_jobs);
+  const unsigned long long batch = pool_batch(n_units * 32ull) >> 5;  // units per cursor update
+  unsigned long long pool_next = 0, pool_end = 0;                     // warp-local batch of units (warp-uniform)
 
   Trav<true, STATS> tr;
   int stack[RT_STACK_SIZE];
-  bool active = false, exhausted = false;
-  unsigned cur_g = 0;
+  tr.idle();
 
   for (;;) {
-    // ---- refill idle lanes with new shadow jobs ----
-    const unsigned idle = __ballot_sync(0xffffffffu, !active);
-    if (idle != 0u && !(exhausted && pool_next >= pool_end)) {
-      if (pool_next >= pool_end && !exhausted) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, RT_POOL_BATCH);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        pool_next = base;
-        pool_end = base + RT_POOL_BATCH < (unsigned long long)n_jobs ? base + RT_POOL_BATCH : (unsigned long long)n_jobs;
-        if (base >= (unsigned long long)n_jobs) { exhausted = true; pool_end = pool_next; }
+    if (pool_next >= pool_end) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(cursor, batch);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= n_units) break;
+      pool_next = base;
+      pool_end = base + batch < n_units ? base + batch : n_units;
+    }
+    const unsigned unit = (unsigned)pool_next;
+    pool_next += 1ull;
+    const int j = (int)(unit / n_chunks);  // warp-uniform
+    const unsigned slot = (unit - (unsigned)j * n_chunks) * 32u + (unsigned)lane;
+    // light and sample of job j (warp-uniform); s < 0: gate ray
+    int l = j, s = -1;
+    if (j >= Lmax) { l = (j - Lmax) / S; s = (j - Lmax) - l * S; }
+    bool active = false, have = false;
+    uint8_t visible = 0;
+    if (slot < n_slots) {
+      const float4 hp = lv.hit_p[slot];
+      const V3 hit = mk(hp);
+      const int iw = __float_as_int(hp.w);
+      V3 src;
+      if (iw & 1) {
+        // mirror child: its light list is the single point it inherited (the parent's hit point)
+        have = l == 0;
+        const int i = iw >> 1;
+        const V3 lp = mk(lv.ray_d[i].w, lv.ray_l[i].x, lv.ray_l[i].y);
+        src = s < 0 ? lp : area_sample(fp, lp, s);
+      } else {
+        have = l < fp.n_lights;
+        src = s < 0 ? ld3(fp.lights + 3 * l)
+                    : (fp.have_sample_table ? ld3(fp.sample_table + 3 * (l * S + s)) : area_sample(fp, ld3(fp.lights + 3 * l), s));
       }
-      const unsigned long long g64 = pool_next + (unsigned long long)__popc(idle & lt_mask);
-      pool_next += (unsigned long long)__popc(idle);
-      if (!active) {
-        if (g64 < pool_end) {
-          // job order: sample-major.  Consecutive jobs are the SAME light sample towards consecutive hit
-          // slots (hits of one 8x4 pixel tile are adjacent in hit_list): a pinhole bundle from the sample
-          // to a small surface patch, far more coherent than the S rays that fan out from one hit point.
-          const unsigned n_slots = (unsigned)n_hits_level;
-          const int j = (int)((unsigned)g64 / n_slots);
-          const unsigned slot = (unsigned)g64 - (unsigned)j * n_slots;
-          const unsigned g = slot * (unsigned)J + (unsigned)j;  // index into vis
-          const int i = lv.hit_list[slot];
-          const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
-          const float2 rl2 = lv.ray_l[i];
-          const RayLights rl = ray_lights(fp, ro, rd, rl2);
-          int l;
-          V3 src = mk(0.f, 0.f, 0.f);
-          bool have = true;
-          if (j < Lmax) {
-            l = j;
-            if (l >= rl.n) have = false; else src = light_pos(fp, rl, l);
-          } else {
-            const int s = j - Lmax;
-            l = s / S;
-            if (l >= rl.n) have = false; else src = light_sample(fp, rl, l, s - l * S, S);
-          }
-          if (!have) {
-            lv.vis[g] = 0;
-          } else {
-            const V3 o = mk(ro), d = mk(rd);
-            const V3 hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
-            const V3 sd = sub(hit, src);                 // :920
-            const V3 rdir = recip_dir(sd);
-            const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, hit, rdir);  // :924
-            traced++;
-            if (tri_enabled || sc.n_spheres > 0) {
-              tr.init(src, sd, hit, tri_enabled, rdir);
-              cur_g = g;
-              active = true;
-            } else {
-              lv.vis[g] = 1;  // nothing can occlude: t stays FLT_MAX >= 0.98 (:946)
-            }
-          }
+      if (have) {
+        const V3 sd = sub(hit, src);  // :920
+        const V3 rdir = recip_dir(sd);
+        const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, hit, rdir);  // :924
+        traced++;
+        visible = 1;  // unless the traversal finds an occluder: t stays FLT_MAX >= 0.98 (:946)
+        if (tri_enabled || sc.n_spheres > 0) {
+          tr.init(src, sd, hit, tri_enabled, rdir);
+          active = true;
         }
       }
     }
-    if (!__any_sync(0xffffffffu, active)) {
-      if (exhausted && pool_next >= pool_end) break;
-      continue;
-    }
-    // ---- traverse (resumes where the lane stopped) ----
-    if (active) {
-      if (tr.run(sc, st, stack, (exhausted && pool_next >= pool_end) ? 1 : refill_below)) {
-        if (tr.finish(sc, st)) {
-          lv.vis[cur_g] = tr.occluded ? 0 : 1;
-          active = false;
-        }
+    // ---- traverse: the whole warp, lanes without a ray idle inside run() ----
+    while (__any_sync(0xffffffffu, active)) {
+      tr.run(sc, st, stack, 0xffffffffu);
+      if (active && tr.finish(sc, st)) {
+        active = false;
+        visible = tr.occluded ? 0 : 1;
       }
     }
-    __syncwarp();
+    if (slot < n_slots) lv.vis[(size_t)slot * (size_t)J + (size_t)j] = visible;
   }
   // census: one atomic per warp
   for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);

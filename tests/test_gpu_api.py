@@ -329,25 +329,6 @@ def test_plain_bvh_mode_is_the_exact_nearest_hit(pkg, oracle_mod, scene_dir):
     print(f"plain BVH vs filtered: {(face != face2).sum()} of {len(face)} sampled pixels differ (reference octree holes)")
 
 
-@pytest.mark.parametrize("refill", [8, 24])
-def test_dynamic_fetch_gives_identical_frames(refill, pkg, scene_dir):
-    capi = pkg.capi
-    capi.init(0)
-    g = load_golden("gallery_area_200x150")
-    arrs = scene_arrays("gallery_area_200x150", pkg, scene_dir)
-    scene = capi.Scene(*arrs)
-    cam = capi.default_camera(200, 150)
-    lights = capi.Lights(g["lights"])
-    p = capi.make_params(200, 150, 1, 0, 3, (4, 4))
-    a = scene.render(cam, lights, p)
-    capi.set_option("refill_below", refill)
-    try:
-        b = scene.render(cam, lights, p)
-    finally:
-        capi.set_option("refill_below", 0)
-    assert (a.rgba == b.rgba).all() and (a.face == b.face).all() and (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
-
-
 def test_unbounded_depth_matches_bounded_when_cap_is_large(pkg, scene_dir):
     """max_depth < 0 (the reference's unbounded recursion, host-synchronised level loop) and a cap
     larger than the scene's natural depth (CUDA-graph path) must give the same frame."""

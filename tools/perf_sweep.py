@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Developer tool: time the frame kernels of a bench workload for several values of a runtime option.
-    python tools/perf_sweep.py --workload c3 --option refill_below --values 0 8 16 24
+    python tools/perf_sweep.py --workload c3 --option leaf_size --values 1 2 4
 Prints per-category kernel milliseconds (CUDA events inside the library), median of --frames frames."""
 import argparse
 import importlib
@@ -17,7 +17,7 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c3")
-    ap.add_argument("--option", default="refill_below")
+    ap.add_argument("--option", default="leaf_size")
     ap.add_argument("--values", type=int, nargs="+", default=[0])
     ap.add_argument("--frames", type=int, default=7)
     ap.add_argument("--recreate", action="store_true", help="re-create the scene per value (build-time options)")
