@@ -502,7 +502,26 @@ def main():
         dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
     dt = float(dt_t.item())
     e2e = {"value": rays_total * k2 / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d) * world,
-           "d2h_bytes_per_step": int(H * W * 4), "ms_per_step": 1e3 * dt / k2, "steps": k2}
+           "d2h_bytes_per_step": int(H * W * 4), "ms_per_step": 1e3 * dt / k2, "steps": k2,
+           "call": "rt_render (blocking, pinned host frame)" if world == 1 else "bands + assembly on rank 0 + D2H"}
+    if world == 1:
+        # the same steps through the streaming call: rt_render_submit / rt_render_wait, two frames in
+        # flight, every frame still copied to pinned host memory inside the timed region
+        hosts = [torch.zeros((rows, W, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+        def pipelined(k):
+            tk = []
+            for i in range(k):
+                if i >= 2:
+                    scene.wait(tk[i - 2])
+                tk.append(scene.submit(cam, lights, params, hosts[i & 1]))
+            scene.wait(tk[-1])
+        pipelined(4)
+        t0 = time.perf_counter()
+        pipelined(k2)
+        dtp = time.perf_counter() - t0
+        assert (hosts[(k2 - 1) & 1] == host_np).all(), "streaming and blocking frames differ"
+        e2e["pipelined"] = {"value": rays_total * k2 / dtp / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * dtp / k2,
+                            "call": "rt_render_submit / rt_render_wait, 2 frames in flight"}
 
     if rank != 0:
         if world > 1:

@@ -181,6 +181,15 @@ int rt_render(RtScene *scene, const RtCamera *cam, const RtLights *lights, const
  * Asynchronous with respect to the host when stats == NULL. */
 int rt_render_device(RtScene *scene, const RtCamera *cam, const RtLights *lights, const RtParams *params,
                      void *d_rgba, int32_t *d_face, float *d_t, float *d_rgb_f32, void *stream, RtStats *stats);
+/* Frame sequences -- the reference re-renders on every camera key (src/main.cpp:59-92) and overlapping
+ * the output of frame k with the tracing of frame k+1 is SURVEY.md 8(f)2.  rt_render_submit queues one
+ * frame plus the device->host copy of its packed RGBA and returns without waiting; *ticket names it.
+ * rt_render_wait blocks until that frame is complete in its rgba_out.  At most two frames are in
+ * flight (double-buffered device frame, copy on its own stream): submitting a third before waiting for
+ * the oldest is RT_ERR_INVALID.  rgba_out should be page-locked; it must stay valid until the wait. */
+int rt_render_submit(RtScene *scene, const RtCamera *cam, const RtLights *lights, const RtParams *params,
+                     uint8_t *rgba_out, int *ticket);
+int rt_render_wait(RtScene *scene, int ticket);
 int rt_local_rows(const RtParams *params);
 /* global row index of each local row (ascending); rows_out has rt_local_rows entries */
 int rt_local_row_map(const RtParams *params, int32_t *rows_out);

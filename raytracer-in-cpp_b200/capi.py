@@ -72,7 +72,7 @@ API_SYMBOLS = [
     "rt_default_params", "rt_mesh_load_obj", "rt_mesh_desc", "rt_mesh_info", "rt_mesh_destroy",
     "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_ref_octree_stats",
     "rt_scene_debug_bvh",
-    "rt_render", "rt_render_device", "rt_local_rows", "rt_local_row_map", "rt_shared_frame_create",
+    "rt_render", "rt_render_device", "rt_render_submit", "rt_render_wait", "rt_local_rows", "rt_local_row_map", "rt_shared_frame_create",
     "rt_shared_frame_open", "rt_shared_frame_close", "rt_device_copy_to_host", "rt_trace_rays",
     "rt_light_strikes", "rt_box_intersect", "rt_box_intersect_box", "rt_ray_triangle", "rt_octree_candidates",
     "rt_phong_shade", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm",
@@ -112,6 +112,8 @@ def lib():
     L.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp, vp, vp]
     L.rt_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp,
                                    vp, vp, vp]
+    L.rt_render_submit.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, C.POINTER(C.c_int)]
+    L.rt_render_wait.argtypes = [vp, C.c_int]
     L.rt_shared_frame_create.argtypes = [C.c_size_t, C.POINTER(vp), vp]
     L.rt_shared_frame_open.argtypes = [vp, C.POINTER(vp)]
     L.rt_shared_frame_close.argtypes = [vp, C.c_int]
@@ -341,6 +343,16 @@ class Scene:
         _check(lib().rt_render(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), _ptr(rgba), _ptr(face),
                                _ptr(t), _ptr(rgb), C.byref(st) if st is not None else None))
         return Frame(rgba, face, t, rgb, st.as_dict() if st is not None else None)
+
+    def submit(self, cam: RtCamera, lights: Lights, params: RtParams, out_rgba: np.ndarray) -> int:
+        """Queue one frame and the copy of its RGBA into out_rgba (ideally pinned); returns a ticket.
+        At most two frames in flight; call wait(ticket) before reading out_rgba."""
+        t = C.c_int(-1)
+        _check(lib().rt_render_submit(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), _ptr(out_rgba), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int) -> None:
+        _check(lib().rt_render_wait(self.h, ticket))
 
     def render_device(self, cam, lights, params, d_rgba: int, d_face: int = 0, d_t: int = 0, d_rgb: int = 0,
                       stream: int = 0, stats: RtStats | None = None):

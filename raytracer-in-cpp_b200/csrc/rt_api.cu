@@ -139,6 +139,12 @@ struct RtScene {
   DevBuf out_rgba, out_face, out_t, out_rgbf, in_a, in_b;
   FrameCounts *h_counts = nullptr;  // pinned mirror
   cudaStream_t stream = nullptr;    // used when the caller passes the (uncapturable) legacy default stream
+  // rt_render_submit / rt_render_wait: two frames in flight
+  cudaStream_t copy_stream = nullptr;
+  DevBuf slot_rgba[2];
+  cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
+  int submit_seq = 0;
   // CUDA graph of the bounded-depth frame (memset + every kernel launch), replayed while its key matches
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<long long> graph_key;
@@ -482,6 +488,12 @@ extern "C" void rt_scene_destroy(RtScene *sc) {
   sc->frame_counts.release(); sc->frame_params.release();
   if (sc->graph_exec) cudaGraphExecDestroy(sc->graph_exec);
   if (sc->stream) cudaStreamDestroy(sc->stream);
+  if (sc->copy_stream) cudaStreamDestroy(sc->copy_stream);
+  for (int k = 0; k < 2; ++k) {
+    if (sc->ev_rendered[k]) cudaEventDestroy(sc->ev_rendered[k]);
+    if (sc->ev_copied[k]) cudaEventDestroy(sc->ev_copied[k]);
+    sc->slot_rgba[k].release();
+  }
   sc->out_rgba.release(); sc->out_face.release(); sc->out_t.release(); sc->out_rgbf.release();
   sc->in_a.release(); sc->in_b.release();
   if (sc->h_counts) cudaFreeHost(sc->h_counts);
@@ -1016,15 +1028,60 @@ extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *light
   RtParams local_p = *p;
   local_p.out_full_frame = 0;  // host outputs always hold this call's rows only
   p = &local_p;
+  // everything on the scene's own stream: frame, copies, one synchronisation at the end
+  cudaStream_t st = sc->stream;
   rc = rt_render_device(sc, cam, lights, p, sc->out_rgba.p, face_out ? sc->out_face.as<int32_t>() : nullptr,
                         t_out ? sc->out_t.as<float>() : nullptr, rgb_f32_out ? sc->out_rgbf.as<float>() : nullptr,
-                        nullptr, stats);
+                        st, stats);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(rgba_out, sc->out_rgba.p, n * 4, cudaMemcpyDeviceToHost, 0));
-  if (face_out) CUDA_TRY(cudaMemcpyAsync(face_out, sc->out_face.p, n * 4, cudaMemcpyDeviceToHost, 0));
-  if (t_out) CUDA_TRY(cudaMemcpyAsync(t_out, sc->out_t.p, n * 4, cudaMemcpyDeviceToHost, 0));
-  if (rgb_f32_out) CUDA_TRY(cudaMemcpyAsync(rgb_f32_out, sc->out_rgbf.p, n * 12, cudaMemcpyDeviceToHost, 0));
-  CUDA_TRY(cudaStreamSynchronize(0));
+  if (n == 0) return RT_OK;
+  CUDA_TRY(cudaMemcpyAsync(rgba_out, sc->out_rgba.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (face_out) CUDA_TRY(cudaMemcpyAsync(face_out, sc->out_face.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (t_out) CUDA_TRY(cudaMemcpyAsync(t_out, sc->out_t.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (rgb_f32_out) CUDA_TRY(cudaMemcpyAsync(rgb_f32_out, sc->out_rgbf.p, n * 12, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return RT_OK;
+}
+
+extern "C" int rt_render_submit(RtScene *sc, const RtCamera *cam, const RtLights *lights, const RtParams *p,
+                                uint8_t *rgba_out, int *ticket) {
+  if (!sc || !p || !rgba_out || !ticket) return fail(RT_ERR_INVALID, "null argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  const int slot = sc->submit_seq & 1;
+  if (sc->slot_busy[slot])
+    return fail(RT_ERR_INVALID, "two frames already in flight: rt_render_wait(ticket %d) first", sc->submit_seq - 2);
+  if (!sc->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    if (!sc->ev_rendered[k]) CUDA_TRY(cudaEventCreateWithFlags(&sc->ev_rendered[k], cudaEventDisableTiming));
+    if (!sc->ev_copied[k]) CUDA_TRY(cudaEventCreateWithFlags(&sc->ev_copied[k], cudaEventDisableTiming));
+  }
+  const size_t n = (size_t)rt_local_rows(p) * (size_t)std::max(0, p->width);
+  if ((rc = sc->slot_rgba[slot].reserve(std::max<size_t>(n, 1) * 4))) return rc;
+  RtParams local_p = *p;
+  local_p.out_full_frame = 0;
+  rc = rt_render_device(sc, cam, lights, &local_p, sc->slot_rgba[slot].p, nullptr, nullptr, nullptr, sc->stream, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(sc->ev_rendered[slot], sc->stream));
+  CUDA_TRY(cudaStreamWaitEvent(sc->copy_stream, sc->ev_rendered[slot], 0));
+  if (n) CUDA_TRY(cudaMemcpyAsync(rgba_out, sc->slot_rgba[slot].p, n * 4, cudaMemcpyDeviceToHost, sc->copy_stream));
+  CUDA_TRY(cudaEventRecord(sc->ev_copied[slot], sc->copy_stream));
+  sc->slot_busy[slot] = true;
+  *ticket = sc->submit_seq++;
+  return RT_OK;
+}
+
+extern "C" int rt_render_wait(RtScene *sc, int ticket) {
+  if (!sc) return fail(RT_ERR_INVALID, "null scene");
+  if (ticket < 0 || ticket >= sc->submit_seq) return fail(RT_ERR_INVALID, "unknown ticket %d", ticket);
+  if (ticket < sc->submit_seq - 2 || !sc->slot_busy[ticket & 1]) return RT_OK;  // already complete
+  if (ticket == sc->submit_seq - 1 && sc->slot_busy[(ticket & 1) ^ 1]) {
+    // frames complete in submission order: finishing the newer one finishes the older one too
+    CUDA_TRY(cudaEventSynchronize(sc->ev_copied[(ticket & 1) ^ 1]));
+    sc->slot_busy[(ticket & 1) ^ 1] = false;
+  }
+  CUDA_TRY(cudaEventSynchronize(sc->ev_copied[ticket & 1]));
+  sc->slot_busy[ticket & 1] = false;
   return RT_OK;
 }
 

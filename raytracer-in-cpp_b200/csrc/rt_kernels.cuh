@@ -306,11 +306,15 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
     }
     const unsigned unit = (unsigned)pool_next;
     pool_next += 1ull;
-    const int j = (int)(unit / n_chunks);  // warp-uniform
-    const unsigned slot = (unit - (unsigned)j * n_chunks) * 32u + (unsigned)lane;
+    const unsigned j = unit / n_chunks;  // warp-uniform
+    const unsigned slot = (unit - j * n_chunks) * 32u + (unsigned)lane;
     // light and sample of job j (warp-uniform); s < 0: gate ray
-    int l = j, s = -1;
-    if (j >= Lmax) { l = (j - Lmax) / S; s = (j - Lmax) - l * S; }
+    int l = (int)j, s = -1;
+    if (j >= (unsigned)Lmax) {
+      const unsigned q = j - (unsigned)Lmax;
+      if (Lmax == 1) { l = 0; s = (int)q; }
+      else { l = (int)(q / (unsigned)S); s = (int)(q - (unsigned)l * (unsigned)S); }
+    }
     bool active = false, have = false;
     uint8_t visible = 0;
     if (slot < n_slots) {
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
         visible = tr.occluded ? 0 : 1;
       }
     }
-    if (slot < n_slots) lv.vis[(size_t)slot * (size_t)J + (size_t)j] = visible;
+    if (slot < n_slots) lv.vis[(size_t)slot * (size_t)J + j] = visible;
   }
   // census: one atomic per warp
   for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);

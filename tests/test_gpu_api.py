@@ -370,3 +370,39 @@ def test_shadow_packets_give_identical_frames(pkg, scene_dir):
             capi.set_option("shadow_packets", 0)
         assert (a.rgba == b.rgba).all() and (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
         assert a.stats["rays_shadow"] == b.stats["rays_shadow"]
+
+
+def test_submit_wait_pipeline_matches_blocking_render(pkg, scene_dir):
+    """rt_render_submit / rt_render_wait (two frames in flight, copy of frame k overlapping the kernels
+    of frame k+1) returns the same frames as the blocking call, in order, for a moving camera."""
+    import torch
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("gallery_area_200x150")
+    arrs = scene_arrays("gallery_area_200x150", pkg, scene_dir)
+    scene = capi.Scene(*arrs)
+    lights = capi.Lights(g["lights"])
+    W, H = 200, 150
+    p = capi.make_params(W, H, 1, 0, 3, (4, 4))
+    cams = []
+    for k in range(5):
+        vi = np.array([[1, 0, 0, 0.05 * k], [0, 1, 0, -0.03 * k], [0, 0, 1, 2.0 + 0.1 * k]], np.float32)
+        cams.append(capi.make_camera((0.05 * k, -0.03 * k, 2.0 + 0.1 * k), vi, (0, 0, W, H), 60.0, np.float32(W) / np.float32(H)))
+    want = [scene.render(c, lights, p, want_face=False, want_t=False, want_rgb=False, want_stats=False).rgba.copy() for c in cams]
+    assert any((want[0] != w).any() for w in want[1:])
+    bufs = [torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+    got, tickets = [], []
+    for k, c in enumerate(cams):
+        if k >= 2:
+            scene.wait(tickets[k - 2])
+            got.append(bufs[k & 1].copy())
+        tickets.append(scene.submit(c, lights, p, bufs[k & 1]))
+    with pytest.raises(RuntimeError):
+        scene.submit(cams[0], lights, p, np.zeros((H, W, 4), np.uint8))  # a third frame in flight
+    scene.wait(tickets[-1])  # completes the older one too
+    got.append(bufs[(len(cams) - 2) & 1].copy())
+    got.append(bufs[(len(cams) - 1) & 1].copy())
+    scene.wait(tickets[0])   # long finished: no-op
+    for k in range(len(cams)):
+        assert (got[k] == want[k]).all(), k
+    scene.close()
