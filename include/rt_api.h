@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 1
+#define RT_API_VERSION 2
 #define RT_MAX_LIGHTS 25   /* bool visibleLights[25], src/flyscene.cpp:699,835 */
 #define RT_MAX_SAMPLES 25
 
@@ -99,6 +99,15 @@ typedef struct {
    * stored at its global position (used to write bands straight into rank 0's framebuffer over an
    * NVLink peer mapping, see rt_shared_frame_*); 0 = d_rgba holds the local rows, packed. */
   int32_t out_full_frame;
+  /* area_light = point_light = 0: the reference's "spherical" light (src/flyscene.cpp:974-993), 25 points
+   * light + R*(sin(phi)cos(theta), sin(phi)sin(theta), cos(phi))/5, theta = 2*pi*u, phi = acos(2u-1).
+   * The reference draws u from a freshly seeded mt19937(random_device) for every point of every shading
+   * call, which no two runs reproduce; here the 25 values of u are fixed per frame:
+   *   u_k = (lowbias32(sphere_seed * 0x9E3779B9u + k) >> 8) / 2^24,  k = 0..24
+   * (lowbias32: x^=x>>16; x*=0x7feb352d; x^=x>>15; x*=0x846ca68b; x^=x>>16), so a frame is a pure function
+   * of its inputs.  sphere_radius = lightrep.getBoundingSphereRadius() (1.0000001f in the reference). */
+  uint32_t sphere_seed;
+  float sphere_radius;
 } RtParams;
 
 typedef struct {
@@ -134,9 +143,7 @@ int rt_device_name(char *buf, size_t n);
 /* runtime knobs: "stats" (0/1 traversal counters), "leaf_size", "persistent_ctas_per_sm",
  * "reference_candidates" (default 1: scenes created afterwards filter BVH hits through the
  * reference's octree candidate sets so that the image matches the reference bit for bit; 0: plain
- * BVH = exact nearest hit over all faces), "shadow_packets" (0, default: every shadow ray is traced on its own; 1: the
- * area-light sample rays of a hit are traced as lockstep packets when the BVH has >= 64 nodes; 2: always),
- * "graph_conditionals" (1, default: empty bounce levels are skipped inside the frame's CUDA graph) */
+ * BVH = exact nearest hit over all faces), "graph_conditionals" (1, default: empty bounce levels are skipped inside the frame's CUDA graph) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);
 

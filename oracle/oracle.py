@@ -67,7 +67,8 @@ class OrParams(C.Structure):
     _fields_ = [("area_light", C.c_int32), ("point_light", C.c_int32), ("max_depth", C.c_int32),
                 ("usteps", C.c_int32), ("vsteps", C.c_int32), ("area_len_x", C.c_float),
                 ("area_len_y", C.c_float), ("light_color", C.c_float * 3), ("capacity", C.c_int32),
-                ("candidates", C.c_int32), ("recursion_guard", C.c_int32)]
+                ("candidates", C.c_int32), ("recursion_guard", C.c_int32), ("sphere_seed", C.c_uint32),
+                ("sphere_radius", C.c_float)]
 
 
 _lib = None
@@ -266,7 +267,7 @@ class Oracle:
     """CPU restatement of the reference render path over a BakedScene."""
 
     def __init__(self, scene: BakedScene, area=0, point=1, max_depth=-1, grid=(5, 5), candidates=0,
-                 capacity=1000, light_color=(1.0, 1.0, 0.0)):
+                 capacity=1000, light_color=(1.0, 1.0, 0.0), sphere_seed=1):
         L = lib()
         self.scene = scene
         self.params = OrParams()
@@ -277,6 +278,7 @@ class Oracle:
         self.params.usteps, self.params.vsteps = int(grid[0]), int(grid[1])
         self.params.candidates = int(candidates)
         self.params.capacity = int(capacity)
+        self.params.sphere_seed = int(sphere_seed)
         for k in range(3):
             self.params.light_color[k] = float(light_color[k])
         self._keep = []

@@ -92,6 +92,8 @@ void or_default_params(OrParams *p) {
   p->capacity = 1000;
   p->candidates = 0;
   p->recursion_guard = 64;
+  p->sphere_seed = 1u;
+  p->sphere_radius = 1.00000012f; /* 0x3f800001, dumped from the reference (tests/golden: light_radius) */
 }
 
 static int node_new(OrScene *s) {
@@ -465,8 +467,15 @@ int or_light_strikes(const OrScene *s, const float hit[3], const float *lights, 
 /* ------------------------------------------------------------------------------------------ */
 /* a12 createSpherePoint / createAreaLight / arealight::getPointLights                         */
 /*     src/flyscene.cpp:956-972, arealight.hpp:15-25.  The random "spherical" mode (:974-995)  */
-/*     seeds from std::random_device and is not reproducible: unsupported (returns 0).         */
+/*     seeds from std::random_device per point and is not reproducible: its 25 draws are       */
+/*     replaced by a counter hash (rt_oracle.h, OrParams.sphere_seed); everything after the     */
+/*     draw follows :981-990 (float randomno/theta/phi/x/y/z, double 2.0f*M_PI*u and acos,      */
+/*     float sin/cos overloads, Vector3f(x,y,z)/5 + lightPoint).  PARITY UNPINNED for this mode.*/
 /* ------------------------------------------------------------------------------------------ */
+static uint32_t hash_lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
 int or_light_samples(const OrParams *p, const float light[3], float *out) {
   if (p->point_light) { out[0] = light[0]; out[1] = light[1]; out[2] = light[2]; return 1; }
   if (p->area_light) {
@@ -485,7 +494,17 @@ int or_light_samples(const OrParams *p, const float light[3], float *out) {
       }
     return k;
   }
-  return 0;
+  for (int k = 0; k < 25; ++k) {
+    uint32_t h = hash_lowbias32(p->sphere_seed * 0x9E3779B9U + (uint32_t)k);
+    float randomno = (float)(h >> 8) * (1.0f / 16777216.0f);
+    float theta = (float)(2.0f * M_PI * randomno);
+    float phi = (float)acos(2.0 * randomno - 1.0);
+    float x = p->sphere_radius * sinf(phi) * cosf(theta);
+    float y = p->sphere_radius * sinf(phi) * sinf(theta);
+    float z = p->sphere_radius * cosf(phi);
+    out[3 * k] = x / 5 + light[0]; out[3 * k + 1] = y / 5 + light[1]; out[3 * k + 2] = z / 5 + light[2];
+  }
+  return 25;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -67,6 +67,10 @@ typedef struct {
   int32_t capacity;      /* octree leaf capacity 1000, src/flyscene.cpp:86 */
   int32_t candidates;    /* 0 = reference octree candidates (faithful); 1 = every face (exact nearest hit) */
   int32_t recursion_guard; /* hard stop for unbounded mode (returns BACKGROUND), default 64 */
+  /* spherical light mode (area_light = point_light = 0, src/flyscene.cpp:974-993): the reference's
+   * random_device draws are replaced by u_k = (lowbias32(seed * 0x9E3779B9u + k) >> 8) / 2^24 */
+  uint32_t sphere_seed;    /* default 1 */
+  float sphere_radius;     /* lightrep.getBoundingSphereRadius(), 1.0000001f in the reference */
 } OrParams;
 
 typedef struct OrScene OrScene;

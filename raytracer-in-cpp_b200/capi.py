@@ -51,7 +51,7 @@ class RtParams(C.Structure):
                 ("point_light", C.c_int32), ("max_depth", C.c_int32), ("usteps", C.c_int32),
                 ("vsteps", C.c_int32), ("area_len_x", C.c_float), ("area_len_y", C.c_float),
                 ("band_rows", C.c_int32), ("band_rank", C.c_int32), ("band_world", C.c_int32),
-                ("out_full_frame", C.c_int32)]
+                ("out_full_frame", C.c_int32), ("sphere_seed", C.c_uint32), ("sphere_radius", C.c_float)]
 
 
 class RtStats(C.Structure):
@@ -159,7 +159,7 @@ def set_option(key: str, value: int):
 
 
 def make_params(width, height, area=0, point=1, max_depth=-1, grid=(5, 5), band_rows=8, band_rank=0,
-                band_world=1) -> RtParams:
+                band_world=1, sphere_seed=1) -> RtParams:
     p = RtParams()
     lib().rt_default_params(C.byref(p))
     p.width, p.height = int(width), int(height)
@@ -167,6 +167,7 @@ def make_params(width, height, area=0, point=1, max_depth=-1, grid=(5, 5), band_
     p.max_depth = int(max_depth)
     p.usteps, p.vsteps = int(grid[0]), int(grid[1])
     p.band_rows, p.band_rank, p.band_world = int(band_rows), int(band_rank), int(band_world)
+    p.sphere_seed = int(sphere_seed)
     return p
 
 

@@ -37,7 +37,6 @@ int g_opt_stats = 0;
 int g_opt_leaf = 2;  // measured best on the 100 k / 1 M-triangle scenes (leaf tests are exact and expensive)
 int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
 int g_opt_ref_candidates = 1;
-int g_opt_shadow_packets = 0;  // 1/2: area-light sample rays traced as lockstep packets (measured slower)
 int g_opt_graph_cond = 1;  // skip empty bounce levels inside the frame graph (conditional nodes)
 
 int fail(int code, const char *fmt, ...) {
@@ -197,7 +196,6 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
   else if (!strcmp(key, "reference_candidates")) g_opt_ref_candidates = value ? 1 : 0;
   else if (!strcmp(key, "graph_conditionals")) g_opt_graph_cond = value ? 1 : 0;
-  else if (!strcmp(key, "shadow_packets")) g_opt_shadow_packets = std::max(0, std::min(2, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
 }
@@ -211,6 +209,8 @@ extern "C" void rt_default_params(RtParams *p) {
   p->usteps = 5; p->vsteps = 5;
   p->area_len_x = 0.3f; p->area_len_y = 0.15f;
   p->band_rows = 8; p->band_rank = 0; p->band_world = 1;
+  p->sphere_seed = 1u;
+  p->sphere_radius = 1.00000012f;  // lightrep.getBoundingSphereRadius() of the reference (0x3f800001)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -565,16 +565,37 @@ extern "C" int rt_local_row_map(const RtParams *p, int32_t *rows_out) {
 
 namespace {
 
+// The 25 sample offsets of the reference's spherical light (createSpherePoint, src/flyscene.cpp:974-993)
+// with the random_device draws replaced by the counter hash documented in rt_api.h (RtParams.sphere_seed).
+// Types follow the reference's expressions: randomno, theta, phi, x, y, z are float; 2.0f * M_PI * randomno
+// and acos(2.0 * randomno - 1.0) are evaluated in double; sin / cos of the float angles resolve to the
+// float overloads (the translation unit is `using namespace std`); Vector3f(x, y, z) / 5 divides by 5.0f.
+constexpr int RT_SPHERE_SAMPLES = 25;
+inline uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+void sphere_offsets(uint32_t seed, float radius, float *out /*[25][3]*/) {
+  for (int k = 0; k < RT_SPHERE_SAMPLES; ++k) {
+    const uint32_t h = lowbias32(seed * 0x9E3779B9U + (uint32_t)k);
+    const float randomno = (float)(h >> 8) * (1.0f / 16777216.0f);
+    const float theta = (float)((double)2.0f * M_PI * (double)randomno);
+    const float phi = (float)std::acos(2.0 * (double)randomno - 1.0);
+    const float x = radius * sinf(phi) * cosf(theta);
+    const float y = radius * sinf(phi) * sinf(theta);
+    const float z = radius * cosf(phi);
+    out[3 * k] = x / 5.0f; out[3 * k + 1] = y / 5.0f; out[3 * k + 2] = z / 5.0f;
+  }
+}
+
 int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, const RtParams *p) {
   memset(&fp, 0, sizeof(fp));
   if (!lights || !p) return fail(RT_ERR_INVALID, "null lights/params");
   if (lights->n < 0 || lights->n > RT_MAX_LIGHTS)
     return fail(RT_ERR_LIMIT, "%d lights: the reference's visibleLights[25] buffer caps lights at %d", lights->n, RT_MAX_LIGHTS);
   if (lights->n > 0 && !lights->pos) return fail(RT_ERR_INVALID, "null light positions");
-  if (!p->point_light && !p->area_light)
-    return fail(RT_ERR_INVALID, "spherical random light mode (areaLight=0, pointLight=0) is not reproducible "
-                                "(std::random_device, src/flyscene.cpp:974-993) and is not supported");
-  if (!p->point_light) {
+  const bool sphere_mode = !p->point_light && !p->area_light;
+  if (p->area_light && !p->point_light) {
     if (p->usteps <= 0 || p->vsteps <= 0 || p->usteps * p->vsteps > RT_MAX_SAMPLES)
       return fail(RT_ERR_LIMIT, "area grid %dx%d exceeds %d samples (visibleLights[25])", p->usteps, p->vsteps, RT_MAX_SAMPLES);
   }
@@ -600,6 +621,12 @@ int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, con
   fp.area_len_x = p->area_len_x; fp.area_len_y = p->area_len_y;
   fp.max_depth = p->max_depth;
   fp.guard_depth = 64;
+  if (sphere_mode) {
+    // 25 samples per light, indexed like a 25 x 1 grid
+    fp.sphere_mode = 1;
+    fp.usteps = RT_SPHERE_SAMPLES; fp.vsteps = 1;
+    sphere_offsets(p->sphere_seed, p->sphere_radius, fp.sphere_off);
+  }
   // area-light sample table for the scene lights (same expression as the device's area_sample)
   fp.have_sample_table = 0;
   if (!p->point_light && p->area_light) {
@@ -670,21 +697,14 @@ constexpr int kAsyncDepth = 8;
 struct FramePlan {
   bool explicit_rays, trav_stats, async;
   int n0, J, Lmax, S, depth_cap;
-  int packet_group;  // 0: every shadow ray through k_shadow; 16 / 32: sample rays as packets of that many lanes
 };
 
-// K2 for one level: gate + sample rays per ray, or gate rays per ray + sample rays as packets
+// K2 for one level: gate + sample rays of every hit
 void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, const LevelBufs &lv, int level, FrameCounts *fc,
                    cudaStream_t st, int grid, int *launches) {
-  const int jobs = pl.packet_group ? pl.Lmax : pl.J;
-  if (pl.trav_stats) k_shadow<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc);
-  else k_shadow<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, jobs, fc);
+  if (pl.trav_stats) k_shadow<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc);
+  else k_shadow<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc);
   *launches += 1;
-  if (pl.packet_group) {
-    if (pl.trav_stats) k_shadow_packet<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, pl.packet_group, fc);
-    else k_shadow_packet<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, pl.packet_group, fc);
-    *launches += 1;
-  }
 }
 
 // enqueue the launches of levels [0, depth_cap] and the folds (async mode: all of them)
@@ -851,9 +871,6 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
   pl.Lmax = std::max(1, fp.n_lights);
   pl.S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
   pl.J = pl.Lmax + pl.Lmax * pl.S;
-  // packets pay off when rays actually walk a tree; on a handful of nodes the per-ray kernel is already converged
-  pl.packet_group = 0;
-  if (g_opt_shadow_packets && pl.S >= 4 && (sc->dev.n_nodes >= 64 || g_opt_shadow_packets == 2)) pl.packet_group = pl.S <= 16 ? 16 : 32;
   if ((unsigned long long)n0 * (unsigned long long)pl.J >= 0xffffffffull)
     return fail(RT_ERR_LIMIT, "%d rays x %d shadow jobs exceed 2^32; render the frame in bands", n0, pl.J);
   pl.async = fp.max_depth >= 0 && fp.max_depth <= kAsyncDepth;
@@ -875,7 +892,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
     for (int l = 0; l <= pl.depth_cap; ++l)
       if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
-    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, pl.packet_group, g_opt_graph_cond,
+    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, g_opt_graph_cond,
                                         (long long)pl.explicit_rays, (long long)pl.trav_stats};
     if (sc->graph_exec == nullptr || key != sc->graph_key) {
       if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
@@ -1302,7 +1319,12 @@ extern "C" int rt_screen_to_world(const RtCamera *cam, int64_t n, const float *p
 extern "C" int rt_light_samples(const RtParams *p, const float light[3], float *out) {
   if (!p || !light || !out) return fail(RT_ERR_INVALID, "null argument");
   if (p->point_light) { out[0] = light[0]; out[1] = light[1]; out[2] = light[2]; return 1; }
-  if (!p->area_light) return fail(RT_ERR_INVALID, "spherical random light mode is not supported");
+  if (!p->area_light) {
+    float off[RT_SPHERE_SAMPLES * 3];
+    sphere_offsets(p->sphere_seed, p->sphere_radius, off);
+    for (int k = 0; k < RT_SPHERE_SAMPLES * 3; ++k) out[k] = off[k] + light[k % 3];
+    return RT_SPHERE_SAMPLES;
+  }
   if (p->usteps * p->vsteps > RT_MAX_SAMPLES) return fail(RT_ERR_LIMIT, "too many samples");
   const float ux = light[0] + p->area_len_x * 1.0f, vy = light[1] + p->area_len_y * 1.0f, uz = light[2] + p->area_len_x * 0.0f;
   int k = 0;

@@ -59,7 +59,6 @@ struct Counters {
 struct FrameCounts {
   unsigned long long work_k1[RT_MAX_LEVELS];  // persistent-kernel work cursors
   unsigned long long work_k2[RT_MAX_LEVELS];
-  unsigned long long work_k2p[RT_MAX_LEVELS];  // packet shadow kernel
   int32_t n_rays[RT_MAX_LEVELS];              // rays queued at level k (k >= 1; level 0 comes as a parameter)
   int32_t n_hits[RT_MAX_LEVELS];              // rays of level k that hit a primitive
   uint32_t k3_done[RT_MAX_LEVELS];            // CTAs of K3(level k) that have finished (last one sets the graph condition)
@@ -215,11 +214,11 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
     }
   }
   if (STATS) {
-    atomicAdd(&fc->ctr.box_tests, (unsigned long long)st.box_tests);
-    atomicAdd(&fc->ctr.tri_tests, (unsigned long long)st.tri_tests);
-    atomicAdd(&fc->ctr.filter_checks, (unsigned long long)st.filter_checks);
-    atomicAdd(&fc->ctr.filter_slow, (unsigned long long)st.filter_slow);
-    atomicAdd(&fc->ctr.filter_rejects, (unsigned long long)st.filter_rejects);
+    warp_sum_add(&fc->ctr.box_tests, st.box_tests);
+    warp_sum_add(&fc->ctr.tri_tests, st.tri_tests);
+    warp_sum_add(&fc->ctr.filter_checks, st.filter_checks);
+    warp_sum_add(&fc->ctr.filter_slow, st.filter_slow);
+    warp_sum_add(&fc->ctr.filter_rejects, st.filter_rejects);
   }
 }
 
@@ -244,6 +243,8 @@ __device__ __forceinline__ V3 light_pos(const FrameParams &fp, const RayLights &
 // arealight::getPointLights (arealight.hpp:15-25) through createAreaLight(light, 0.3, 0.15, u, v)
 // (src/flyscene.cpp:956-972): sample k = i*vsteps + j, i outer.
 __device__ __forceinline__ V3 area_sample(const FrameParams &fp, V3 c, int k) {
+  // spherical mode (:974-993): Vector3f(x, y, z) / 5 + lightPoint, offsets from the host
+  if (fp.sphere_mode) return add(ld3(fp.sphere_off + 3 * k), c);
   const int i = k / fp.vsteps, j = k - i * fp.vsteps;
   const float ux = c.x + fp.area_len_x * 1.0f;  // uvec = corner + lengthX*(1,0,0)
   const float vy = c.y + fp.area_len_y * 1.0f;  // vvec = corner + lengthY*(0,1,0)
@@ -273,20 +274,18 @@ __device__ __forceinline__ V3 light_sample(const FrameParams &fp, const RayLight
 // surface patch, far more coherent than the S rays that fan out from one hit point; and at any moment
 // all warps of the GPU work on the same one or two samples, which keeps the upper tree levels of that
 // bundle in L1.  j is warp-uniform, the per-job set-up is one 16-byte load of the hit point (hit_p).
-// jobs_per_slot == J: gate and sample rays of every hit; jobs_per_slot == Lmax: gate rays only (the
-// sample rays are then traced as packets by k_shadow_packet).
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const FrameParams *__restrict__ fpp,
                                                const LevelBufs lv, const int level, const int J, const int Lmax,
-                                               const int S, const int jobs_per_slot, FrameCounts *fc) {
+                                               const int S, FrameCounts *fc) {
   RT_STAGE_FRAME_PARAMS(fpp);
   const int lane = threadIdx.x & 31;
   TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   unsigned traced = 0;
   const unsigned n_slots = (unsigned)fc->n_hits[level];
   const unsigned n_chunks = (n_slots + 31u) >> 5;
-  const unsigned long long n_units = (unsigned long long)n_chunks * (unsigned long long)jobs_per_slot;
+  const unsigned long long n_units = (unsigned long long)n_chunks * (unsigned long long)J;
   unsigned long long *cursor = &fc->work_k2[level];
   const unsigned long long batch = pool_batch(n_units * 32ull) >> 5;  // units per cursor update
   unsigned long long pool_next = 0, pool_end = 0;                     // warp-local batch of units (warp-uniform)
@@ -359,160 +358,14 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
   for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
   if (lane == 0 && traced) atomicAdd(&fc->ctr.shadow_rays, (unsigned long long)traced);
   if (STATS) {
-    atomicAdd(&fc->ctr.box_tests_k2, (unsigned long long)st.box_tests);
-    atomicAdd(&fc->ctr.tri_tests_k2, (unsigned long long)st.tri_tests);
-    atomicAdd(&fc->ctr.filter_checks, (unsigned long long)st.filter_checks);
-    atomicAdd(&fc->ctr.filter_slow, (unsigned long long)st.filter_slow);
-    atomicAdd(&fc->ctr.filter_rejects, (unsigned long long)st.filter_rejects);
+    warp_sum_add(&fc->ctr.box_tests_k2, st.box_tests);
+    warp_sum_add(&fc->ctr.tri_tests_k2, st.tri_tests);
+    warp_sum_add(&fc->ctr.filter_checks, st.filter_checks);
+    warp_sum_add(&fc->ctr.filter_slow, st.filter_slow);
+    warp_sum_add(&fc->ctr.filter_rejects, st.filter_rejects);
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K2p: area-light sample rays as PACKETS.  The S sample rays of one (hit, light) pair end in the same
-// surface point and start within the small light grid, so they want the same BVH nodes.  A group of
-// G lanes (16 or 32, S <= G) walks the tree in lockstep: one node for the whole group, visited if ANY
-// lane's ray hits its box (ballot), children ordered by the group's first live lane, every live lane
-// tests the leaf's primitives against its own ray.  All lanes of a group take identical decisions, so
-// each keeps its own copy of the (identical) traversal stack and no shared memory is needed.  Lanes
-// whose ray is occluded drop out of the votes; the group ends when its stack is empty or no lane is
-// live.  The octree candidate filter is applied inline at each actual triangle hit (fast-accept path).
-// Result: no lane divergence in the box tests at all, at the price of a few box tests a single ray
-// would have skipped.
-// ---------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_shadow_packet(const DevScene sc, const FrameParams *__restrict__ fpp,
-                                                      const LevelBufs lv, const int level, const int J, const int Lmax,
-                                                      const int S, const int G, FrameCounts *fc) {
-  RT_STAGE_FRAME_PARAMS(fpp);
-  const int lane = threadIdx.x & 31;
-  const int gl = lane & (G - 1), group_lane0 = lane - gl, group_in_warp = lane / G;
-  const int groups_per_warp = 32 / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << group_lane0);
-  TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
-  unsigned traced = 0;
-  const unsigned n_packets = (unsigned)fc->n_hits[level] * (unsigned)Lmax;
-  unsigned long long *cursor = &fc->work_k2p[level];
-  int stack[RT_STACK_SIZE];
-  const Excluded no_ex = {0, -1, -1, -1, -1};
-
-  for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)groups_per_warp);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= (unsigned long long)n_packets) break;
-    const unsigned pk = (unsigned)base + (unsigned)group_in_warp;
-    // ---- per-lane ray set-up ----
-    bool live = false;        // this lane's ray is still looking for an occluder
-    unsigned vis_index = 0;
-    bool have_job = false;
-    V3 src = mk(0, 0, 0), sd = mk(0, 0, 0), hit = mk(0, 0, 0);
-    bool tri_enabled = false;
-    if (pk < n_packets && gl < S) {
-      const unsigned slot = pk / (unsigned)Lmax;
-      const int l = (int)(pk - slot * (unsigned)Lmax);
-      const int i = lv.hit_list[slot];
-      const float4 ro = lv.ray_o[i], rd = lv.ray_d[i];
-      const float2 rl2 = lv.ray_l[i];
-      const RayLights rl = ray_lights(fp, ro, rd, rl2);
-      vis_index = slot * (unsigned)J + (unsigned)(Lmax + l * S + gl);
-      if (l >= rl.n) {
-        lv.vis[vis_index] = 0;
-      } else {
-        have_job = true;
-        src = light_sample(fp, rl, l, gl, S);
-        const V3 o = mk(ro), d = mk(rd);
-        hit = add(o, mul(lv.hit_t[i], d));  // src/flyscene.cpp:695
-        sd = sub(hit, src);                 // :920
-        tri_enabled = ref_box_intersect(sc.root_min, sc.root_max, src, hit);  // :924
-        traced++;
-        live = tri_enabled || sc.n_spheres > 0;
-        if (!(sd.x == sd.x) || !(sd.y == sd.y) || !(sd.z == sd.z)) live = false;  // NaN ray: never hits
-      }
-    }
-    bool occluded = false;
-    const float ooeps = 1.0e-24f;
-    const float idx = 1.0f / (fabsf(sd.x) > ooeps ? sd.x : copysignf(ooeps, sd.x));
-    const float idy = 1.0f / (fabsf(sd.y) > ooeps ? sd.y : copysignf(ooeps, sd.y));
-    const float idz = 1.0f / (fabsf(sd.z) > ooeps ? sd.z : copysignf(ooeps, sd.z));
-    const float oox = src.x * idx, ooy = src.y * idy, ooz = src.z * idz;
-
-    // ---- lockstep traversal: `node`, `sp` and the stack contents are identical across the group ----
-    int sp = 0;
-    int node = 0;  // >= 0 inner pair node, < 0 leaf code, RT_SENTINEL = done
-    if ((__ballot_sync(0xffffffffu, live) & gmask) == 0u) node = RT_SENTINEL;
-    while (__any_sync(0xffffffffu, node != RT_SENTINEL)) {
-      const bool group_on = node != RT_SENTINEL;
-      bool h0 = false, h1 = false;
-      float t0n = 0.f, t1n = 0.f;
-      int c0 = RT_SENTINEL, c1 = RT_SENTINEL;
-      if (group_on && node >= 0) {
-        const float4 *np = sc.nodes + (size_t)node * 4;
-        const float4 q0 = __ldg(np + 0), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-        const float4 q3f = __ldg(np + 3);
-        c0 = __float_as_int(q3f.x); c1 = __float_as_int(q3f.y);
-        if (live) {
-          if (STATS) st.box_tests += 2;
-          const float a0x = fmaf(q0.x, idx, -oox), b0x = fmaf(q0.y, idx, -oox);
-          const float a0y = fmaf(q0.z, idy, -ooy), b0y = fmaf(q0.w, idy, -ooy);
-          const float a0z = fmaf(q2.x, idz, -ooz), b0z = fmaf(q2.y, idz, -ooz);
-          t0n = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.f));
-          const float t0f = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), 0.98f));
-          const float a1x = fmaf(q1.x, idx, -oox), b1x = fmaf(q1.y, idx, -oox);
-          const float a1y = fmaf(q1.z, idy, -ooy), b1y = fmaf(q1.w, idy, -ooy);
-          const float a1z = fmaf(q2.z, idz, -ooz), b1z = fmaf(q2.w, idz, -ooz);
-          t1n = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.f));
-          const float t1f = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), 0.98f));
-          h0 = t0f >= t0n; h1 = t1f >= t1n;
-        }
-      } else if (group_on && node < 0) {
-        // ---- leaf: every live lane tests the primitives against its own ray ----
-        if (live) {
-          float bt = RT_NO_HIT_T; int bi = -1;
-          if (intersect_leaf<true, STATS>(sc, node, src, sd, hit, tri_enabled, bt, bi, st, no_ex, true)) {
-            occluded = true;
-            live = false;
-          }
-        }
-      }
-      // ---- group votes (all 32 lanes take part; each group reads its own bits) ----
-      const unsigned m0 = __ballot_sync(0xffffffffu, h0) & gmask;
-      const unsigned m1 = __ballot_sync(0xffffffffu, h1) & gmask;
-      const unsigned mlive = __ballot_sync(0xffffffffu, live) & gmask;
-      // ordering: the child nearer the surface point first, judged by the group's first live lane
-      const int first = mlive ? (__ffs(mlive) - 1) : group_lane0;
-      const float f0 = __shfl_sync(0xffffffffu, t0n, first), f1 = __shfl_sync(0xffffffffu, t1n, first);
-      if (group_on) {
-        if (mlive == 0u) {
-          node = RT_SENTINEL;  // every ray of the packet is occluded (or had nothing to do)
-        } else if (node >= 0) {
-          if (m0 == 0u && m1 == 0u) {
-            node = sp > 0 ? stack[--sp] : RT_SENTINEL;
-          } else {
-            int nxt = m0 ? c0 : c1;
-            if (m0 && m1) {
-              int other = c1;
-              if (f1 > f0) { nxt = c1; other = c0; }
-              stack[sp++] = other;
-            }
-            node = nxt;
-          }
-        } else {
-          node = sp > 0 ? stack[--sp] : RT_SENTINEL;  // leaf done
-        }
-      }
-    }
-    if (have_job) lv.vis[vis_index] = occluded ? 0 : 1;
-  }
-  for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
-  if (lane == 0 && traced) atomicAdd(&fc->ctr.shadow_rays, (unsigned long long)traced);
-  if (STATS) {
-    atomicAdd(&fc->ctr.box_tests_k2, (unsigned long long)st.box_tests);
-    atomicAdd(&fc->ctr.tri_tests_k2, (unsigned long long)st.tri_tests);
-    atomicAdd(&fc->ctr.filter_checks, (unsigned long long)st.filter_checks);
-    atomicAdd(&fc->ctr.filter_slow, (unsigned long long)st.filter_slow);
-    atomicAdd(&fc->ctr.filter_rejects, (unsigned long long)st.filter_rejects);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // shading helpers

@@ -211,6 +211,7 @@ RtParams Flyscene::params(int w, int h) const {
   p.area_light = areaLight; p.point_light = pointLight;
   p.max_depth = max_depth;
   p.usteps = usteps; p.vsteps = vsteps;
+  p.sphere_seed = sphere_seed;
   return p;
 }
 
@@ -300,7 +301,14 @@ arealight Flyscene::createAreaLight(Vector3f corner, float lengthX, float length
 std::vector<Vector3f> Flyscene::createSpherePoint(Vector3f lightPoint) {
   if (pointLight) return {lightPoint};
   if (areaLight) return createAreaLight(lightPoint, 0.3f, 0.15f, usteps, vsteps).getPointLights();
-  throw std::runtime_error("spherical random light mode is not reproducible (std::random_device) and not supported");
+  // spherical mode (src/flyscene.cpp:974-993) with the documented deterministic draws (RtParams.sphere_seed)
+  const RtParams p = params(1, 1);
+  float out[25 * 3];
+  const int n = rt_light_samples(&p, lightPoint.data(), out);
+  if (n < 0) throw std::runtime_error(rt_last_error());
+  std::vector<Vector3f> pts;
+  for (int k = 0; k < n; ++k) pts.push_back(Vector3f(out[3 * k], out[3 * k + 1], out[3 * k + 2]));
+  return pts;
 }
 
 }  // namespace rt

@@ -147,6 +147,7 @@ class Flyscene {
   void setLightMode(bool area, bool point) { areaLight = area; pointLight = point; mode_set = true; }
   void setMaxDepth(int d) { max_depth = d; }
   void setAreaGrid(int u, int v) { usteps = u; vsteps = v; }
+  void setSphereSeed(uint32_t s) { sphere_seed = s; }  // spherical light mode: RtParams.sphere_seed
 
   Flycamera *getCamera() { return &flycamera; }
   void addLight() { lights.push_back(flycamera.getCenter()); }
@@ -178,6 +179,7 @@ class Flyscene {
   std::string model_path = "resources/models/cube.obj";  // src/flyscene.cpp:51
   bool areaLight = false, pointLight = true, mode_set = false;
   int max_depth = -1, usteps = 5, vsteps = 5;
+  uint32_t sphere_seed = 1;
   float light_color[3] = {1.f, 1.f, 0.f};  // lightrep.setColor, src/flyscene.cpp:68
   std::vector<uint8_t> frame;
 };

@@ -19,6 +19,7 @@ int main(int argc, char **argv) {
   std::string scene = "resources/models/cube.obj";
   int W = 1000, H = 1000, area = -1, point = -1, depth = -1, gu = 5, gv = 5, frames = 1, device = 0;
   float rx = 0, ry = 0, tx = 0, ty = 0, tz = 0;
+  uint32_t sphere_seed = 1;
   std::vector<rt::Vector3f> extra_lights;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -38,6 +39,7 @@ int main(int argc, char **argv) {
     else if (a == "--cam-trans") { tx = atof(next()); ty = atof(next()); tz = atof(next()); }
     else if (a == "--frames") frames = atoi(next());
     else if (a == "--device") device = atoi(next());
+    else if (a == "--sphere-seed") sphere_seed = (uint32_t)strtoul(next(), nullptr, 10);
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
   }
   try {
@@ -47,6 +49,7 @@ int main(int argc, char **argv) {
     if (area >= 0 || point >= 0) fs.setLightMode(area > 0, point != 0);
     fs.setMaxDepth(depth);
     fs.setAreaGrid(gu, gv);
+    fs.setSphereSeed(sphere_seed);
     fs.initialize(W, H);
     for (const auto &l : extra_lights) fs.getLights().push_back(l);
     if (rx != 0 || ry != 0) fs.getCamera()->setRotation(rx, ry);

@@ -163,8 +163,6 @@ def test_limits_and_errors(pkg, scene_dir):
         scene.render(cam, capi.Lights(np.zeros((26, 3), np.float32)), capi.make_params(32, 32))
     with pytest.raises(capi.RtError):  # 6 x 5 grid > 25 samples
         scene.render(cam, capi.Lights(np.zeros((1, 3), np.float32)), capi.make_params(32, 32, 1, 0, -1, (6, 5)))
-    with pytest.raises(capi.RtError):  # random spherical light mode
-        scene.render(cam, capi.Lights(np.zeros((1, 3), np.float32)), capi.make_params(32, 32, 0, 0))
     # empty scene and zero lights render (all background / all shadow)
     empty = capi.Scene(np.zeros((0, 3, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3, 3), np.float32),
                        np.zeros(0, np.int32), g["mats"])
@@ -348,28 +346,6 @@ def test_unbounded_depth_matches_bounded_when_cap_is_large(pkg, scene_dir):
     for _ in range(3):
         c = scene.render(cam, lights, capi.make_params(160, 120, 0, 1, 8), want_stats=False)
         assert (c.rgba == b.rgba).all()
-
-
-def test_shadow_packets_give_identical_frames(pkg, scene_dir):
-    """The optional packet traversal of area-light sample rays (k_shadow_packet) is a pure scheduling
-    change: same visibility bits, same frame."""
-    capi = pkg.capi
-    capi.init(0)
-    g = load_golden("gallery_area_200x150")
-    arrs = scene_arrays("gallery_area_200x150", pkg, scene_dir)
-    scene = capi.Scene(*arrs)
-    cam = capi.default_camera(200, 150)
-    lights = capi.Lights(g["lights"])
-    for grid in [(4, 4), (5, 5), (3, 2)]:
-        p = capi.make_params(200, 150, 1, 0, 3, grid)
-        a = scene.render(cam, lights, p)
-        capi.set_option("shadow_packets", 2)
-        try:
-            b = scene.render(cam, lights, p)
-        finally:
-            capi.set_option("shadow_packets", 0)
-        assert (a.rgba == b.rgba).all() and (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
-        assert a.stats["rays_shadow"] == b.stats["rays_shadow"]
 
 
 def test_submit_wait_pipeline_matches_blocking_render(pkg, scene_dir):

@@ -80,7 +80,7 @@ def test_library_exports_every_declared_symbol(pkg):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, f"librt_b200.so does not export {missing}"
     assert declared == set(pkg.capi.API_SYMBOLS)
-    assert pkg.capi.lib().rt_api_version() == 1
+    assert pkg.capi.lib().rt_api_version() == 2
 
 
 def test_no_cpu_fallback(pkg):
@@ -136,8 +136,15 @@ def test_light_samples_host(pkg):
     assert np.allclose(s[0], (-0.0700000003, 0.114999995, 1), atol=1e-8)
     assert np.allclose(s[24], (-0.629999995, 1.03499997, 1), atol=1e-8)
     assert capi.light_samples(capi.make_params(10, 10, area=0, point=1), (3, 4, 5)).tolist() == [[3, 4, 5]]
-    with pytest.raises(capi.RtError):
-        capi.light_samples(capi.make_params(10, 10, area=0, point=0), (0, 0, 0))  # random spherical mode
+    # spherical mode (src/flyscene.cpp:974-993) with deterministic draws: 25 points on the sphere of
+    # radius R/5 around the light, a pure function of (seed, light)
+    L = np.array((-1, 1, 1), np.float32)
+    sp = capi.light_samples(capi.make_params(10, 10, area=0, point=0), L)
+    assert sp.shape == (25, 3)
+    assert np.allclose(np.linalg.norm(sp.astype(np.float64) - L, axis=1), 1.0000001 / 5, atol=2e-7)
+    assert (sp == capi.light_samples(capi.make_params(10, 10, area=0, point=0), L)).all()
+    assert (sp != capi.light_samples(capi.make_params(10, 10, area=0, point=0, sphere_seed=2), L)).any()
+    assert len(np.unique(sp, axis=0)) == 25
     with pytest.raises(capi.RtError):
         capi.light_samples(capi.make_params(10, 10, area=1, point=0, grid=(6, 5)), (0, 0, 0))  # > 25 samples
 
@@ -168,3 +175,21 @@ def test_reference_octree_shape(case, pkg):
     out = np.zeros(4, np.int64)
     assert capi.lib().rt_ref_octree_stats(C.byref(d), 1000, out.ctypes.data) == 0
     assert (out == g["octree_stats"]).all(), (out, g["octree_stats"])
+
+
+def test_spherical_light_samples_library_equals_oracle(pkg, oracle_mod):
+    """The deterministic replacement of the reference's random spherical light: the library's host code
+    and the oracle restate the same expression (src/flyscene.cpp:981-990) -> identical floats."""
+    import ctypes as C
+    O = oracle_mod
+    capi = pkg.capi
+    for seed in (1, 2, 12345, 0xFFFFFFFF):
+        for light in ((-1, 1, 1), (0.25, -3.5, 2.0)):
+            l = np.array(light, np.float32)
+            got = capi.light_samples(capi.make_params(8, 8, area=0, point=0, sphere_seed=seed), l)
+            p = O.OrParams()
+            O.lib().or_default_params(C.byref(p))
+            p.area_light, p.point_light, p.sphere_seed = 0, 0, seed
+            want = np.zeros((25, 3), np.float32)
+            assert O.lib().or_light_samples(C.byref(p), l.ctypes.data, want.ctypes.data) == 25
+            assert (got.view(np.uint32) == want.view(np.uint32)).all()
