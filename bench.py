@@ -43,7 +43,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s at 1080p (primary + shadow + secondary rays per second, reference ray census)"
-BAND_ROWS = 8
+BAND_ROWS = 8  # minimum band height; see band_rows_for()
+
+
+def band_rows_for(height, world):
+    """Interleaved band height: every rank gets about 8 bands (load balance across the image) that are as
+    tall as that allows (a rank then touches ~1/world of the scene instead of all of it; measured with
+    tools/band_sweep.py: 8K frame on 8 ranks 0.84 -> 0.76 ms per rank going from 8- to 64-row bands)."""
+    return max(BAND_ROWS, (height // (max(world, 1) * 8)) & ~7)
 
 WORKLOADS = {
     "c1": dict(desc="bundled cube.obj 1000x1000, point light, natural depth (BASELINE configs[0])",
@@ -300,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--band-rows", type=int, default=0, help="multi-GPU band height; 0 = band_rows_for(H, world)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -345,7 +353,8 @@ def main():
     W, H = wl["w"], wl["h"]
     cam = capi.default_camera(W, H)
     lights = capi.Lights(np.array([[-1.0, 1.0, 1.0]], np.float32))  # src/flyscene.cpp:72
-    params = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], BAND_ROWS, rank, world)
+    band_rows = args.band_rows or band_rows_for(H, world)
+    params = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], band_rows, rank, world)
     rows = capi.lib().rt_local_rows(C.byref(params))
     gather = BandGather(capi.local_row_map(params), W, H, rank, world, dist, torch, dev) if world > 1 else None
     max_rows = gather.max_rows if gather else rows
@@ -376,7 +385,7 @@ def main():
             dist.broadcast(hbuf, src=0)
             if rank != 0:
                 shared = capi.SharedFrame(W, H, bytes(hbuf.cpu().numpy().tobytes()))
-            params_peer = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], BAND_ROWS, rank, world)
+            params_peer = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], band_rows, rank, world)
             params_peer.out_full_frame = 1
             token = torch.zeros(1, dtype=torch.int32, device=dev)
 
@@ -593,7 +602,7 @@ def main():
                    "spheres": int(0 if spheres is None else len(spheres)), "lights": 1,
                    "samples_per_light": 1 if wl["point"] else wl["grid"][0] * wl["grid"][1],
                    "max_depth": wl["max_depth"], "l2": "flushed between timed frames (512 MiB memset)",
-                   "parallelism": (f"{world} x interleaved {BAND_ROWS}-row bands; " +
+                   "parallelism": (f"{world} x interleaved {band_rows}-row bands; " +
                                    ("kernels store pixels into rank 0's framebuffer over NVLink peer memory (CUDA IPC), "
                                     "4-byte NCCL all-reduce as completion signal" if nccl_line else "NCCL gather to rank 0"))
                    if world > 1 else "1 GPU",
