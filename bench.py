@@ -612,7 +612,7 @@ def main():
                          "in point mode the identical gate/sample ray is traced and counted once"},
         "mpix_per_s": W * H * args.steps / (ms_total * 1e-3) / 1e6,
         "work": {k: stats[k] for k in ("box_tests", "tri_tests", "box_tests_shadow", "tri_tests_shadow", "shade_samples",
-                                         "filter_checks", "filter_slow", "filter_rejects")},
+                                         "filter_checks", "filter_slow", "filter_rejects", "shadow_rays_traced")},
         "kernel_ms": kernel_ms, "gpu_launches": int(stats["kernel_launches"] * args.steps),
         "clocks": clocks, "wall_s": wall, "nccl_gather_baseline": nccl_line, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

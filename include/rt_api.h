@@ -112,7 +112,8 @@ typedef struct {
 
 typedef struct {
   int64_t rays_primary;     /* one per rendered pixel */
-  int64_t rays_shadow;      /* any-hit queries traced (gate + sample rays; merged in point mode) */
+  int64_t rays_shadow;      /* any-hit queries of the reference's census: L gate rays per hit + L*S sample rays
+                               for the hits whose gate passed (src/flyscene.cpp:699-710,836); merged in point mode */
   int64_t rays_secondary;   /* reflection / refraction / pass-through rays */
   int64_t pixels;           /* pixels rendered by this call */
   int32_t levels;           /* bounce levels executed */
@@ -127,6 +128,9 @@ typedef struct {
   int64_t box_tests_shadow, tri_tests_shadow;
   /* reference-candidate filter: winners checked, checks that needed the exact octree walk, rejections */
   int64_t filter_checks, filter_slow, filter_rejects;
+  /* any-hit queries the shadow kernel actually traced ("stats" option): it skips the sample rays of a hit
+   * once that hit's gate result is known to be "no light visible", and may trace a few before it is */
+  int64_t shadow_rays_traced;
 } RtStats;
 
 typedef struct RtScene RtScene;   /* device-resident BVH + triangle soup + shading tables */

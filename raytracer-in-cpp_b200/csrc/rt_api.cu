@@ -995,6 +995,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     stats->rays_primary = n0;
     stats->pixels = n0;
     stats->rays_shadow = (int64_t)h.ctr.shadow_rays;
+    stats->shadow_rays_traced = (int64_t)h.ctr.shadow_rays_traced;
     int64_t secondary = 0;
     int lv_used = 1;
     for (int l = 1; l < RT_MAX_LEVELS; ++l) { secondary += h.n_rays[l]; if (h.n_rays[l] > 0) lv_used = l + 1; }

@@ -19,6 +19,8 @@
 namespace rtd {
 
 // record types written by K3 and consumed by K3b
+#define RT_HIT_DARK 0x40000000  // hit_p.w flag: the hit's only light is occluded, its sample rays are moot
+
 enum RecType : uint8_t {
   REC_TERMINAL = 0,        // rec.xyz is the final colour of this ray
   REC_MIRROR = 1,          // 0.15*P + 0.85*child                  illum 3,4   :738
@@ -44,7 +46,8 @@ struct LevelBufs {
 };
 
 struct Counters {
-  unsigned long long shadow_rays;
+  unsigned long long shadow_rays;         // reference census (K3)
+  unsigned long long shadow_rays_traced;  // any-hit queries K2 actually traced (stats builds)
   unsigned long long secondary_rays;
   unsigned long long box_tests;      // K1 (nearest hit)
   unsigned long long tri_tests;      // K1
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
       if (iw & 1) {
         // mirror child: its light list is the single point it inherited (the parent's hit point)
         have = l == 0;
-        const int i = iw >> 1;
+        const int i = (iw & ~RT_HIT_DARK) >> 1;
         const V3 lp = mk(lv.ray_d[i].w, lv.ray_l[i].x, lv.ray_l[i].y);
         src = s < 0 ? lp : area_sample(fp, lp, s);
       } else {
@@ -332,6 +335,12 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
         src = s < 0 ? ld3(fp.lights + 3 * l)
                     : (fp.have_sample_table ? ld3(fp.sample_table + 3 * (l * S + s)) : area_sample(fp, ld3(fp.lights + 3 * l), s));
       }
+      // Sample rays of a hit whose gate failed are never looked at (SHADOW, src/flyscene.cpp:699-710: the
+      // reference returns before phongShade).  For hits with a single light the gate unit leaves a flag
+      // in hit_p.w (below); gate units precede all sample units in the unit order, so a sample unit
+      // almost always sees it and skips the ray.  Seeing a stale copy only costs a ray nobody uses: the
+      // frame does not depend on the timing.
+      if (s >= 0 && (iw & RT_HIT_DARK)) have = false;
       if (have) {
         const V3 sd = sub(hit, src);  // :920
         const V3 rdir = recip_dir(sd);
@@ -352,11 +361,19 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
         visible = tr.occluded ? 0 : 1;
       }
     }
-    if (slot < n_slots) lv.vis[(size_t)slot * (size_t)J + j] = visible;
+    if (slot < n_slots) {
+      lv.vis[(size_t)slot * (size_t)J + j] = visible;
+      if (j == 0u && S > 0 && visible == 0) {
+        // gate ray of light 0 occluded: if it is the hit's only light, flag the hit
+        int *w = reinterpret_cast<int *>(lv.hit_p + slot) + 3;
+        const int iw = *w;
+        if ((iw & 1) || fp.n_lights == 1) *w = iw | RT_HIT_DARK;
+      }
+    }
   }
-  // census: one atomic per warp
-  for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
-  if (lane == 0 && traced) atomicAdd(&fc->ctr.shadow_rays, (unsigned long long)traced);
+  // rays actually traced (work; the census is counted by K3): a few sample rays of dark hits may have
+  // been traced before their gate result was visible
+  if (STATS) warp_sum_add(&fc->ctr.shadow_rays_traced, traced);
   if (STATS) {
     warp_sum_add(&fc->ctr.box_tests_k2, st.box_tests);
     warp_sum_add(&fc->ctr.tri_tests_k2, st.tri_tests);
@@ -499,7 +516,7 @@ __global__ void __launch_bounds__(128, 8) k_shade(const DevScene sc, const Frame
   float *rgb_f32 = level == 0 ? fp.out_rgbf : nullptr;
   const int n_hits = fc->n_hits[level];
   const int n_round = (n_hits + 31) & ~31;
-  unsigned samples_shaded = 0;
+  unsigned samples_shaded = 0, shadow_asked = 0;
   for (int slot_in = blockIdx.x * blockDim.x + threadIdx.x; slot_in < n_round; slot_in += gridDim.x * blockDim.x) {
     const bool valid = slot_in < n_hits;
     const int i = valid ? lv.hit_list[slot_in] : 0;
@@ -519,6 +536,9 @@ __global__ void __launch_bounds__(128, 8) k_shade(const DevScene sc, const Frame
       const uint8_t *vis = lv.vis + (size_t)slot_in * J;
       bool any = false;
       for (int l = 0; l < rl.n; ++l) any = any || (vis[l] != 0);
+      // ray census with the reference's semantics: L gate rays per hit, L*S sample rays only if the gate
+      // passed (src/flyscene.cpp:699-710,836); in point mode (S = 0) the sample ray IS the gate ray
+      shadow_asked += (unsigned)(rl.n + (any ? rl.n * S : 0));
       if (!any) {
         colour = mk(0.f, 0.f, 0.f);  // SHADOW, :699-710
       } else {
@@ -592,8 +612,21 @@ __global__ void __launch_bounds__(128, 8) k_shade(const DevScene sc, const Frame
       if (rgb_f32) { rgb_f32[3 * (size_t)i] = colour.x; rgb_f32[3 * (size_t)i + 1] = colour.y; rgb_f32[3 * (size_t)i + 2] = colour.z; }
     }
   }
-  for (int off = 16; off > 0; off >>= 1) samples_shaded += __shfl_down_sync(0xffffffffu, samples_shaded, off);
-  if ((threadIdx.x & 31) == 0 && samples_shaded) atomicAdd(&fc->ctr.shade_samples, (unsigned long long)samples_shaded);
+  // counters: warp shuffle -> shared -> one global atomic per CTA and counter
+  __shared__ unsigned s_count[2];
+  if (threadIdx.x < 2) s_count[threadIdx.x] = 0u;
+  __syncthreads();
+  for (int off = 16; off > 0; off >>= 1) {
+    samples_shaded += __shfl_down_sync(0xffffffffu, samples_shaded, off);
+    shadow_asked += __shfl_down_sync(0xffffffffu, shadow_asked, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (samples_shaded) atomicAdd(&s_count[0], samples_shaded);
+    if (shadow_asked) atomicAdd(&s_count[1], shadow_asked);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_count[0]) atomicAdd(&fc->ctr.shade_samples, (unsigned long long)s_count[0]);
+  if (threadIdx.x == 1 && s_count[1]) atomicAdd(&fc->ctr.shadow_rays, (unsigned long long)s_count[1]);
   // CUDA-graph replay: the last CTA to finish tells the graph whether the next bounce level has any
   // rays; if not, the conditional node that holds that level's kernels (and everything deeper) is skipped
   if (next_level_cond != 0) {

@@ -73,13 +73,21 @@ def test_full_frame_matches_oracle(case, pkg, capi, oracle_mod, scene_dir):
     orc = O.Oracle(O.BakedScene(verts, fn, vn, mid, mats, g["model_matrix"]), area=cp["area"], point=cp["point"],
                    max_depth=cp["max_depth"], grid=cp["grid"], light_color=g["light_color"])
     ocam = O.Oracle.camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    orc.census(reset=True)
     pxy, rgb, face, t, rgb8 = orc.render(ocam, g["lights"], cp["w"], cp["h"], stride=1, threads=8)
+    n_prim, n_shadow, n_sec = [int(x) for x in orc.census(reset=True)]
     px, py = pxy[:, 0], pxy[:, 1]
     assert (fr.face[py, px] == face).all()
     assert (fr.t[py, px].view(np.uint32) == t.view(np.uint32)).all()
     err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - quant(rgb)).max(-1)
     assert (err <= 1).mean() >= 0.999, f"max err {err.max()}"
-    print(f"{case}: full frame {len(px)} px, rgb8 exact {(err == 0).mean():.6f}, max err {int(err.max())}")
+    # ray census (the "ray" of Mrays/s): the kernels' counts equal the reference-semantics census of the
+    # oracle; illum 6/7 child rays the reference traces and discards are the documented exception
+    print(f"{case}: full frame {len(px)} px, rgb8 exact {(err == 0).mean():.6f}, max err {int(err.max())}; census gpu "
+          f"{fr.stats['rays_primary']}/{fr.stats['rays_shadow']}/{fr.stats['rays_secondary']} oracle {n_prim}/{n_shadow}/{n_sec}")
+    assert fr.stats["rays_primary"] == n_prim == len(px)
+    if case != "gallery_area_200x150":
+        assert fr.stats["rays_shadow"] == n_shadow and fr.stats["rays_secondary"] == n_sec
     scene.close()
 
 
