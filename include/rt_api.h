@@ -246,6 +246,12 @@ int rt_screen_to_world(const RtCamera *cam, int64_t n, const float *pixels_xy, f
 int rt_light_samples(const RtParams *params, const float light[3], float *out /*[25][3]*/);
 
 /* ---- output -------------------------------------------------------------------------------- */
+/* Device self-test of the shading kernels' shared-reciprocal vector division (x/n, y/n, z/n with one
+ * reciprocal; must equal IEEE division bit for bit): n_trials random operand sets, exponents within
+ * +-exp_range of 1.0 (exp_range <= 0: unrestricted bit patterns incl. zero, denormal, inf, NaN).
+ * *mismatches receives the number of trials whose three quotients are not all identical. */
+int rt_selftest_div3(int64_t n_trials, uint32_t seed, int32_t exp_range, int64_t *mismatches);
+
 /* Tucano::ImageImporter::writePPMImage (tucano/utils/ppmIO.hpp:130-151): ASCII P3, "r g b " per
  * pixel, one text line per image row.  binary != 0 writes P6 instead. */
 int rt_write_ppm(const char *path, const uint8_t *rgba, int32_t width, int32_t height, int32_t binary);

@@ -76,7 +76,7 @@ API_SYMBOLS = [
     "rt_render", "rt_render_device", "rt_render_submit", "rt_render_wait", "rt_local_rows", "rt_local_row_map", "rt_shared_frame_create",
     "rt_shared_frame_open", "rt_shared_frame_close", "rt_device_copy_to_host", "rt_trace_rays",
     "rt_light_strikes", "rt_box_intersect", "rt_box_intersect_box", "rt_ray_triangle", "rt_octree_candidates",
-    "rt_phong_shade", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm",
+    "rt_phong_shade", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm", "rt_selftest_div3",
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def lib():
     L.rt_screen_to_world.argtypes = [C.POINTER(RtCamera), i64, f32p, vp]
     L.rt_light_samples.argtypes = [C.POINTER(RtParams), vp, vp]
     L.rt_write_ppm.argtypes = [C.c_char_p, vp, i32, i32, i32]
+    L.rt_selftest_div3.argtypes = [i64, C.c_uint32, i32, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -427,6 +428,12 @@ def screen_to_world(cam: RtCamera, pixels_xy):
     out = np.zeros((p.shape[0], 3), np.float32)
     _check(lib().rt_screen_to_world(C.byref(cam), p.shape[0], _ptr(p), _ptr(out)))
     return out
+
+
+def selftest_div3(n_trials: int, seed: int, exp_range: int) -> int:
+    bad = C.c_int64(-1)
+    _check(lib().rt_selftest_div3(int(n_trials), int(seed), int(exp_range), C.byref(bad)))
+    return bad.value
 
 
 def light_samples(params: RtParams, light):

@@ -1339,6 +1339,23 @@ extern "C" int rt_light_samples(const RtParams *p, const float light[3], float *
   return k;
 }
 
+// Device self-test: div3 (the shared-reciprocal normalisation of the shading kernels) against IEEE division
+extern "C" int rt_selftest_div3(int64_t n_trials, uint32_t seed, int32_t exp_range, int64_t *mismatches) {
+  if (!mismatches || n_trials < 0) return fail(RT_ERR_INVALID, "bad argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  unsigned long long *d_bad = nullptr;
+  CUDA_TRY(cudaMalloc(&d_bad, 8));
+  cudaMemset(d_bad, 0, 8);
+  k_selftest_div3<<<g_sm_count * 8, 256>>>((unsigned long long)n_trials, seed, exp_range, d_bad);
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, d_bad, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+  *mismatches = (int64_t)h;
+  return RT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // output: writePPMImage, tucano/utils/ppmIO.hpp:130-151
 // ---------------------------------------------------------------------------------------------

@@ -797,4 +797,38 @@ __global__ void __launch_bounds__(128) k_phong_shade(const DevScene sc, const Fr
   }
 }
 
+// self-test of div3 (rt_device.cuh) against IEEE division: trial k draws a divisor and three numerators from
+// a counter hash -- uniformly random bit patterns, exponents confined to the given range around 1 for the
+// "typical" trials, unrestricted patterns (incl. zero, denormal, inf, NaN) otherwise
+__device__ __forceinline__ unsigned selftest_hash(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__global__ void k_selftest_div3(const unsigned long long n_trials, const unsigned seed, const int exp_range,
+                                unsigned long long *mismatches) {
+  unsigned long long bad = 0;
+  for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n_trials;
+       k += (unsigned long long)gridDim.x * blockDim.x) {
+    float v[4];
+    for (int c = 0; c < 4; ++c) {
+      unsigned h = selftest_hash(seed ^ selftest_hash((unsigned)(k >> 32) * 0x9E3779B9U + (unsigned)k * 4u + (unsigned)c));
+      if (exp_range > 0) {
+        const unsigned ex = 127u - (unsigned)exp_range + (selftest_hash(h) % (2u * (unsigned)exp_range + 1u));
+        h = (h & 0x807fffffu) | (ex << 23);
+        if ((k & 15ull) == (unsigned long long)c) h &= 0x80000000u;  // sprinkle signed zeros over the numerators
+      }
+      v[c] = __int_as_float((int)h);
+    }
+    if (exp_range > 0 && v[0] == 0.f) v[0] = 1.5f;
+    const V3 q = div3(mk(v[1], v[2], v[3]), v[0]);
+    const float ex0 = v[1] / v[0], ex1 = v[2] / v[0], ex2 = v[3] / v[0];
+    // NaN results must be NaN on both sides; everything else bit-identical (signed zeros included)
+    const bool ok0 = (ex0 != ex0) ? (q.x != q.x) : (__float_as_int(q.x) == __float_as_int(ex0));
+    const bool ok1 = (ex1 != ex1) ? (q.y != q.y) : (__float_as_int(q.y) == __float_as_int(ex1));
+    const bool ok2 = (ex2 != ex2) ? (q.z != q.z) : (__float_as_int(q.z) == __float_as_int(ex2));
+    if (!(ok0 && ok1 && ok2)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace rtd

@@ -382,3 +382,13 @@ def test_submit_wait_pipeline_matches_blocking_render(pkg, scene_dir):
     for k in range(len(cams)):
         assert (got[k] == want[k]).all(), k
     scene.close()
+
+
+def test_shared_reciprocal_division_is_ieee_exact(pkg):
+    """normalized() in the shading kernels divides a 3-vector by its norm with ONE refined reciprocal
+    (rt_device.cuh div3).  On the device: 2^31 random operand sets per exponent window, plus unrestricted
+    bit patterns (zero, denormal, inf, NaN), every quotient compared bitwise with IEEE division."""
+    capi = pkg.capi
+    capi.init(0)
+    for seed, exp_range in [(1, 2), (2, 20), (3, 59), (4, 70), (5, 0), (6, 126)]:
+        assert capi.selftest_div3(1 << 31, seed, exp_range) == 0, (seed, exp_range)
