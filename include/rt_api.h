@@ -18,6 +18,10 @@
  * Every function returns 0 on success or a negative RtStatus; rt_last_error() gives the message
  * (thread-local).  There is NO CPU fallback: without a CUDA device every compute entry point fails
  * with RT_ERR_NO_DEVICE.  All calls are blocking unless a stream is passed.
+ *
+ * Threading: like the reference, whose raytraceScene() is called from the main thread and blocks
+ * (SURVEY.md 8b), the library is driven by ONE host thread per process; one process per GPU
+ * (rt_init selects the device).  Options (rt_set_option) and the per-scene workspaces are not locked.
  */
 #ifndef RT_API_H
 #define RT_API_H
@@ -175,6 +179,12 @@ int rt_scene_info(const RtScene *scene, int64_t *n_nodes, int64_t *n_leaves, int
 /* Shape of the reference octree for this scene (BoxTree, capacity 1000, depth 15): out[4] =
  * reachable leaves, inner nodes, face references, largest leaf.  Host only (no GPU needed). */
 int rt_ref_octree_stats(const RtSceneDesc *desc, int32_t capacity, int64_t out[4]);
+/* Host only (no GPU needed): builds the BVH rt_scene_create would build over the triangles of desc with
+ * at most leaf_size triangles per leaf and verifies what the device traversal relies on -- every face in
+ * exactly one leaf, every leaf box containing its faces, every child box inside its parent's, every node
+ * reachable once, depth within the traversal stack.  out[6] = nodes, leaves, depth, largest leaf, faces
+ * referenced, 1000 x SAH cost.  RT_ERR_INVALID (+ message) names the first violated invariant. */
+int rt_bvh_check(const RtSceneDesc *desc, int32_t leaf_size, int64_t out[6]);
 /* debug / test access to the flattened BVH (host copies): nodes [n_nodes][16] floats as uploaded,
  * tri_face [n_tris] original face id of each soup slot */
 int rt_scene_debug_bvh(const RtScene *scene, float *nodes, int64_t nodes_cap, int32_t *tri_face, int64_t tri_cap);

@@ -72,7 +72,7 @@ API_SYMBOLS = [
     "rt_api_version", "rt_init", "rt_shutdown", "rt_last_error", "rt_device_name", "rt_set_option",
     "rt_default_params", "rt_mesh_load_obj", "rt_mesh_desc", "rt_mesh_info", "rt_mesh_destroy",
     "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_ref_octree_stats",
-    "rt_scene_debug_bvh",
+    "rt_scene_debug_bvh", "rt_bvh_check",
     "rt_render", "rt_render_device", "rt_render_submit", "rt_render_wait", "rt_local_rows", "rt_local_row_map", "rt_shared_frame_create",
     "rt_shared_frame_open", "rt_shared_frame_close", "rt_device_copy_to_host", "rt_trace_rays",
     "rt_light_strikes", "rt_box_intersect", "rt_box_intersect_box", "rt_ray_triangle", "rt_octree_candidates",
@@ -110,6 +110,7 @@ def lib():
     L.rt_scene_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rt_scene_debug_bvh.argtypes = [vp, vp, i64, vp, i64]
     L.rt_ref_octree_stats.argtypes = [C.POINTER(RtSceneDesc), i32, vp]
+    L.rt_bvh_check.argtypes = [C.POINTER(RtSceneDesc), i32, vp]
     L.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp, vp, vp]
     L.rt_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp, vp,
                                    vp, vp, vp]
@@ -428,6 +429,18 @@ def screen_to_world(cam: RtCamera, pixels_xy):
     out = np.zeros((p.shape[0], 3), np.float32)
     _check(lib().rt_screen_to_world(C.byref(cam), p.shape[0], _ptr(p), _ptr(out)))
     return out
+
+
+def bvh_check(verts, leaf_size=2):
+    """Host-only BVH build + invariant check; returns dict(nodes, leaves, depth, max_leaf, refs, sah)."""
+    v = np.ascontiguousarray(verts, np.float32)
+    d = RtSceneDesc()
+    d.n_faces = int(v.reshape(-1, 9).shape[0]) if v.size else 0
+    d.verts = _ptr(v)
+    out = np.zeros(6, np.int64)
+    _check(lib().rt_bvh_check(C.byref(d), int(leaf_size), _ptr(out)))
+    return dict(nodes=int(out[0]), leaves=int(out[1]), depth=int(out[2]), max_leaf=int(out[3]), refs=int(out[4]),
+                sah=out[5] / 1000.0)
 
 
 def selftest_div3(n_trials: int, seed: int, exp_range: int) -> int:

@@ -298,10 +298,17 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
                 desc->n_spheres, desc->n_materials);
   if (desc->n_faces > 0 && (!desc->verts || !desc->face_normals || !desc->vertex_normals || !desc->material_id))
     return fail(RT_ERR_INVALID, "null face arrays");
-  int rc = ensure_device();
-  if (rc) return rc;
-  const auto t_start = std::chrono::high_resolution_clock::now();
-
+  if (desc->n_spheres > 0 && (!desc->spheres || !desc->sphere_material)) return fail(RT_ERR_INVALID, "null sphere arrays");
+  if (!desc->materials) return fail(RT_ERR_INVALID, "null material array");
+  // geometry must be finite: the acceleration structure sorts and bins coordinates
+  for (size_t k = 0; k < (size_t)desc->n_faces * 9; ++k)
+    if (!std::isfinite(desc->verts[k]))
+      return fail(RT_ERR_INVALID, "face %zu has a non-finite vertex coordinate", k / 9);
+  for (size_t k = 0; k < (size_t)desc->n_spheres; ++k) {
+    const float *sp = desc->spheres + 4 * k;
+    if (!std::isfinite(sp[0]) || !std::isfinite(sp[1]) || !std::isfinite(sp[2]) || !std::isfinite(sp[3]) || sp[3] < 0.f)
+      return fail(RT_ERR_INVALID, "sphere %zu is not finite or has a negative radius", k);
+  }
   const int T = desc->n_faces, S = desc->n_spheres, N = T + S;
   for (int i = 0; i < T; ++i)
     if (desc->material_id[i] < 0 || desc->material_id[i] >= desc->n_materials)
@@ -309,6 +316,9 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
   for (int i = 0; i < S; ++i)
     if (desc->sphere_material[i] < 0 || desc->sphere_material[i] >= desc->n_materials)
       return fail(RT_ERR_INVALID, "sphere %d has a bad material id", i);
+  int rc = ensure_device();
+  if (rc) return rc;
+  const auto t_start = std::chrono::high_resolution_clock::now();
 
   RtScene *sc = new RtScene();
   // ---- reference root box: BoundingBox(Mesh&), src/boundingBox.cpp:14-43 (max starts at FLT_MIN) ----
@@ -523,6 +533,80 @@ extern "C" int rt_ref_octree_stats(const RtSceneDesc *desc, int32_t capacity, in
   if (desc->n_faces > 0 && !desc->verts) return fail(RT_ERR_INVALID, "null verts");
   const rt::RefOctree oct = rt::build_ref_octree(desc->verts, desc->n_faces, capacity, 15, 0);
   out[0] = oct.n_leaves; out[1] = oct.n_inner; out[2] = oct.n_refs; out[3] = oct.max_leaf;
+  return RT_OK;
+}
+
+// Host only: build the BVH rt_scene_create would build for the triangles of desc and check the
+// invariants the device traversal relies on.
+extern "C" int rt_bvh_check(const RtSceneDesc *desc, int32_t leaf_size, int64_t out[6]) {
+  if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
+  if (desc->n_faces < 0 || (desc->n_faces > 0 && !desc->verts)) return fail(RT_ERR_INVALID, "bad face arrays");
+  const int T = desc->n_faces;
+  std::vector<rt::Aabb> boxes((size_t)T);
+  std::vector<uint8_t> kind((size_t)T, 0);
+  for (int i = 0; i < T; ++i) {
+    const float *v = desc->verts + (size_t)i * 9;
+    for (int a = 0; a < 3; ++a) {
+      if (!std::isfinite(v[a]) || !std::isfinite(v[3 + a]) || !std::isfinite(v[6 + a]))
+        return fail(RT_ERR_INVALID, "face %d has a non-finite vertex coordinate", i);
+      boxes[i].mn[a] = std::min(v[a], std::min(v[3 + a], v[6 + a]));
+      boxes[i].mx[a] = std::max(v[a], std::max(v[3 + a], v[6 + a]));
+    }
+  }
+  const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const rt::BvhBuildResult bvh = rt::build_bvh(boxes, kind, leaf_size, 0.f, threads);
+  if ((int)bvh.prim_order.size() != T) return fail(RT_ERR_INVALID, "prim_order has %zu entries for %d faces", bvh.prim_order.size(), T);
+  // every node is reached once from the root, every soup slot lies in exactly one leaf, every leaf's box
+  // (as stored in its parent) contains its primitives, every child box lies inside its parent's
+  std::vector<uint8_t> seen_prim((size_t)T, 0), seen_node(bvh.nodes.size(), 0), seen_slot((size_t)T, 0);
+  struct Item { int32_t node; int depth; float mn[3], mx[3]; };
+  std::vector<Item> todo;
+  const float inf = std::numeric_limits<float>::infinity();
+  todo.push_back({0, 1, {-inf, -inf, -inf}, {inf, inf, inf}});
+  int64_t n_leaves = 0, max_leaf = 0, max_depth = 0, refs = 0;
+  while (!todo.empty()) {
+    const Item it = todo.back();
+    todo.pop_back();
+    if (it.node < 0 || (size_t)it.node >= bvh.nodes.size()) return fail(RT_ERR_INVALID, "child index %d out of range", it.node);
+    if (seen_node[(size_t)it.node]++) return fail(RT_ERR_INVALID, "node %d reached twice", it.node);
+    max_depth = std::max<int64_t>(max_depth, it.depth);
+    const rt::PairNode &pn = bvh.nodes[(size_t)it.node];
+    for (int c = 0; c < 2; ++c) {
+      int32_t code;
+      memcpy(&code, &pn.q[12 + c], 4);
+      if (code == rt::kEmptyLeaf) continue;
+      const float mn[3] = {pn.q[4 * c + 0], pn.q[4 * c + 2], pn.q[8 + 2 * c]};
+      const float mx[3] = {pn.q[4 * c + 1], pn.q[4 * c + 3], pn.q[9 + 2 * c]};
+      for (int a = 0; a < 3; ++a)
+        if (!(mn[a] <= mx[a]) || mn[a] < it.mn[a] || mx[a] > it.mx[a])
+          return fail(RT_ERR_INVALID, "node %d child %d: box not inside its parent's", it.node, c);
+      if (code >= 0) {
+        Item ch{code, it.depth + 1, {mn[0], mn[1], mn[2]}, {mx[0], mx[1], mx[2]}};
+        todo.push_back(ch);
+        continue;
+      }
+      const uint32_t lc = (uint32_t)~code;
+      const int first = (int)(lc >> 5), count = (int)(lc & 15u) + 1;
+      ++n_leaves;
+      max_leaf = std::max<int64_t>(max_leaf, count);
+      if (first < 0 || first + count > T) return fail(RT_ERR_INVALID, "leaf range [%d,%d) outside the soup", first, first + count);
+      for (int k = first; k < first + count; ++k) {
+        if (seen_slot[(size_t)k]++) return fail(RT_ERR_INVALID, "soup slot %d in two leaves", k);
+        const int p = bvh.prim_order[(size_t)k];
+        if (p < 0 || p >= T || seen_prim[(size_t)p]++) return fail(RT_ERR_INVALID, "face %d referenced twice or out of range", p);
+        ++refs;
+        for (int a = 0; a < 3; ++a)
+          if (boxes[(size_t)p].mn[a] < mn[a] || boxes[(size_t)p].mx[a] > mx[a])
+            return fail(RT_ERR_INVALID, "face %d sticks out of its leaf box", p);
+      }
+    }
+  }
+  if (refs != T) return fail(RT_ERR_INVALID, "%lld of %d faces are in leaves", (long long)refs, T);
+  for (size_t i = 0; i < seen_node.size(); ++i)
+    if (!seen_node[i]) return fail(RT_ERR_INVALID, "node %zu is unreachable", i);
+  if (max_depth > RT_STACK_SIZE - 4) return fail(RT_ERR_INVALID, "tree depth %lld exceeds the traversal stack", (long long)max_depth);
+  out[0] = (int64_t)bvh.nodes.size(); out[1] = n_leaves; out[2] = max_depth; out[3] = max_leaf; out[4] = refs;
+  out[5] = (int64_t)(bvh.sah_cost * 1000.0);
   return RT_OK;
 }
 

@@ -193,3 +193,55 @@ def test_spherical_light_samples_library_equals_oracle(pkg, oracle_mod):
             want = np.zeros((25, 3), np.float32)
             assert O.lib().or_light_samples(C.byref(p), l.ctypes.data, want.ctypes.data) == 25
             assert (got.view(np.uint32) == want.view(np.uint32)).all()
+
+
+def test_scene_validation_precedes_device_work(pkg):
+    """Bad scene descriptions are rejected with a message before any CUDA call (so also on a CPU-only box):
+    non-finite geometry, material ids outside the table, negative sphere radii."""
+    from conftest import load_golden
+    capi = pkg.capi
+    g = load_golden("cube_point_1000")
+    good = (g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    v = g["verts"].copy()
+    v[3, 1, 2] = np.nan
+    with pytest.raises(capi.RtError, match="non-finite"):
+        capi.Scene(v, *good[1:])
+    v[3, 1, 2] = np.inf
+    with pytest.raises(capi.RtError, match="non-finite"):
+        capi.Scene(v, *good[1:])
+    mid = g["mat_id"].copy()
+    mid[5] = g["mats"].shape[0]
+    with pytest.raises(capi.RtError, match="material id"):
+        capi.Scene(good[0], good[1], good[2], mid, good[4])
+    with pytest.raises(capi.RtError, match="negative radius"):
+        capi.Scene(*good, None, np.array([[0, 0, 0, -1.0]], np.float32), np.zeros(1, np.int32))
+
+
+def test_bvh_builder_invariants_host_only(pkg):
+    """host/bvh_builder.cpp through rt_bvh_check (no GPU): every face in exactly one leaf, boxes nested,
+    depth within the device stack -- on a regular height field, on heavily clustered and duplicated
+    triangles (SAH degenerates: the depth guard must switch to median splits) and on tiny inputs."""
+    capi = pkg.capi
+    sc = pkg.scenes
+    hv, hf = sc.heightfield_mesh(64)
+    rng = np.random.default_rng(5)
+    cases = {"heightfield": np.asarray(hv, np.float32)[hf].reshape(-1, 9)}
+    tri = rng.uniform(-1, 1, (1, 9)).astype(np.float32)
+    cases["4000 copies of one triangle"] = np.repeat(tri, 4000, axis=0)
+    c = rng.uniform(-1, 1, (3000, 1, 3)).astype(np.float32) ** 7  # clustered towards the origin
+    cases["clustered"] = (c + rng.normal(0, 1e-4, (3000, 3, 3)).astype(np.float32)).reshape(-1, 9)
+    big = rng.uniform(-1, 1, (500, 9)).astype(np.float32)
+    big[::50] *= 1e4  # a few huge triangles among small ones
+    cases["mixed sizes"] = big
+    cases["one"] = tri
+    cases["none"] = np.zeros((0, 9), np.float32)
+    for name, v in cases.items():
+        for leaf in (1, 2, 4, 16):
+            r = capi.bvh_check(v, leaf)
+            assert r["refs"] == v.shape[0], name
+            assert r["max_leaf"] <= leaf or v.shape[0] == 0, (name, r)
+            assert r["depth"] <= 60, (name, r)
+    with pytest.raises(capi.RtError, match="non-finite"):
+        bad = cases["mixed sizes"].copy()
+        bad[7, 4] = np.nan
+        capi.bvh_check(bad)
