@@ -63,6 +63,18 @@ int main(int argc, char **argv) {
     rt::BoundingBox bb(rt::Vector3f(-0.25f, -0.25f, -0.25f), rt::Vector3f(0.25f, 0.25f, 0.25f));
     printf("\"bb_hit\": %d,\n\"bb_miss\": %d,\n", (int)bb.boxIntersect(origin, rt::Vector3f(0, 0, 0)),
            (int)bb.boxIntersect(origin, rt::Vector3f(3, 3, 0)));
+    // the headless debug ray (recursiveDebugRay, src/flyscene.cpp:241-430): chain of mirror bounces
+    std::vector<rt::DebugRayLevel> dbg = fs.debugRay(px, py, 3, false);
+    printf("\"debug_ray\": [");
+    for (size_t k = 0; k < dbg.size(); ++k) {
+      const rt::DebugRayLevel &lv = dbg[k];
+      printf("%s{\"level\": %d, \"face\": %d, \"t\": %.9g, \"origin\": [%.9g, %.9g, %.9g], \"direction\": [%.9g, %.9g, %.9g], "
+             "\"colour\": [%.9g, %.9g, %.9g], \"visible\": [%d, %d]}",
+             k ? ", " : "", lv.level, lv.face, lv.t, lv.origin.x, lv.origin.y, lv.origin.z, lv.direction.x, lv.direction.y,
+             lv.direction.z, lv.colour.x, lv.colour.y, lv.colour.z, lv.face >= 0 ? (int)lv.light_visible[0] : -1,
+             lv.face >= 0 ? (int)lv.light_visible[1] : -1);
+    }
+    printf("],\n");
     std::vector<int64_t> st = fs.octree.stats();
     printf("\"octree\": [%lld, %lld, %lld, %lld]\n}\n", (long long)st[0], (long long)st[1], (long long)st[2], (long long)st[3]);
   } catch (const std::exception &e) {

@@ -292,6 +292,75 @@ bool Flyscene::lightStrikes(Vector3f &hitPoint, std::vector<Vector3f> &lts, bool
   return any;
 }
 
+std::vector<DebugRayLevel> Flyscene::debugRay(float px, float py, int maxDepth, bool print) {
+  std::vector<DebugRayLevel> out;
+  std::vector<float> lp;
+  for (const Vector3f &l : lights) { lp.push_back(l.x); lp.push_back(l.y); lp.push_back(l.z); }
+  RtLights L{};
+  L.n = (int32_t)lights.size();
+  L.pos = lp.data();
+  memcpy(L.color, light_color, sizeof(light_color));
+  const Vector3f eye = flycamera.getCenter();
+  Vector3f pos = eye;
+  Vector3f dir = flycamera.screenToWorld(px, py) - eye;  // src/flyscene.cpp:434-441
+  for (int n = 0; n <= maxDepth; ++n) {
+    DebugRayLevel lv;
+    lv.level = n;
+    lv.origin = pos;
+    lv.direction = dir;
+    RtParams p = params(1, 1);
+    if (p.max_depth >= 0) p.max_depth = std::max(0, p.max_depth - n);
+    float rgb[3];
+    int32_t face = -1;
+    float t = 0.f;
+    check(rt_trace_rays(octree.handle(), 1, pos.data(), dir.data(), &L, &p, rgb, &face, &t), "debugRay");
+    lv.colour = Vector3f(rgb);
+    lv.face = face;
+    lv.t = t;
+    if (face < 0 || face >= desc.n_faces) { out.push_back(lv); break; }
+    lv.hit = pos + t * dir;
+    lv.normal = Vector3f(desc.face_normals + 3 * (size_t)face);
+    lv.reflected = dir - (2.f * dot(dir, lv.normal)) * lv.normal;  // :349
+    lv.shininess = desc.materials[desc.material_id[face]].ns;
+    if (!lights.empty()) {
+      std::vector<uint8_t> vis(lights.size());
+      check(rt_light_strikes(octree.handle(), 1, lv.hit.data(), &L, vis.data()), "lightStrikes");
+      for (size_t i = 0; i < lights.size(); ++i) {
+        const Vector3f dl = normalized(lv.hit - lights[i]);                         // :384
+        lv.light_visible.push_back(vis[i] != 0);
+        lv.cos_theta.push_back(dot(dl, lv.normal));                                  // :386
+        lv.cos_phi.push_back(dot(normalized(-1.f * (lv.hit - eye)), lv.reflected));  // :387
+      }
+    }
+    out.push_back(lv);
+    pos = lv.hit;
+    dir = lv.reflected;
+  }
+  if (print) {
+    for (const DebugRayLevel &lv : out) {
+      if (lv.face < 0) break;
+      std::cout << "\n-------------------------------------------------------------\n"
+                << "                      DEBUG RAY INFO (level = " << lv.level << ")\n"
+                << "                      ==============                       \n\n";
+      auto pv = [](const char *k, const Vector3f &v) { std::cout << k << "(" << v.x << ", " << v.y << ", " << v.z << ")\n"; };
+      pv(" Hitpoint = ", lv.hit);
+      std::cout << " Distance = " << norm(lv.hit - eye) << "\n";
+      pv(" Normal vector = ", lv.normal);
+      pv(" Reflection vector = ", lv.reflected);
+      pv(" Color rendered = ", lv.colour);
+      std::cout << " shininess = " << lv.shininess << "\n\n LIGHTS INFO                    \n";
+      for (size_t i = 0; i < lv.cos_theta.size(); ++i)
+        std::cout << " ----light " << i << " ----\n visible = " << (int)lv.light_visible[i] << "\n cos (Theta) = " << lv.cos_theta[i]
+                  << "\n cos (Phi)   = " << lv.cos_phi[i] << "\n";
+      std::cout << "\n HIT TRIANGLE INFO                    \n";
+      for (int k = 0; k < 3; ++k) pv(k == 0 ? "                   Vertex 1 = " : k == 1 ? "                   Vertex 2 = " : "                   Vertex 3 = ",
+                                     Vector3f(desc.verts + 9 * (size_t)lv.face + 3 * k));
+      std::cout << "-------------------------------------------------------------" << std::endl;
+    }
+  }
+  return out;
+}
+
 arealight Flyscene::createAreaLight(Vector3f corner, float lengthX, float lengthY, int us, int vs) {
   Vector3f uvec = corner + lengthX * Vector3f(1, 0, 0);  // src/flyscene.cpp:957-958: points, not edge vectors
   Vector3f vvec = corner + lengthY * Vector3f(0, 1, 0);

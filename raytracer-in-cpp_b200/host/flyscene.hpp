@@ -134,6 +134,18 @@ struct Face {  // Tucano::Face as the ray tracer reads it
   Vector3f normal;
 };
 
+// One level of the debug ray (the fields of the reference's "DEBUG RAY INFO" console dump,
+// src/flyscene.cpp:364-407)
+struct DebugRayLevel {
+  int level = 0;
+  int face = -1;            // -1: this segment left the scene
+  float t = 0.f;
+  Vector3f origin, direction, hit, normal, reflected, colour;
+  float shininess = 0.f;
+  std::vector<bool> light_visible;          // lightStrikes per light
+  std::vector<float> cos_theta, cos_phi;    // per light, as printed by the reference
+};
+
 class Flyscene {
  public:
   Flyscene() {}
@@ -164,6 +176,12 @@ class Flyscene {
   float rayTriangleIntersection(Vector3f &rayPoint, Vector3f &rayDirection, Face &triangle);
   Vector3f phongShade(Vector3f &origin, Vector3f &hitPoint, Face &triangle, std::vector<Vector3f> &lights);
   bool lightStrikes(Vector3f &hitPoint, std::vector<Vector3f> &lights, bool visibleLights[]);
+  // Headless counterpart of recursiveDebugRay (src/flyscene.cpp:241-430): follows the ray through pixel
+  // (px, py) and its mirror reflections for up to maxDepth bounces with single-ray GPU queries and returns
+  // what the reference prints per level (its cylinder / sphere gizmos are GL and out of scope).  Unlike the
+  // reference -- which re-tests every level against the camera->pixel candidate set -- each level is a proper
+  // traceRay from the previous hit point.  print = true writes the reference's console layout to stdout.
+  std::vector<DebugRayLevel> debugRay(float px, float py, int maxDepth, bool print = false);
   arealight createAreaLight(Vector3f corner, float lengthX, float lengthY, int usteps, int vsteps);
   std::vector<Vector3f> createSpherePoint(Vector3f lightPoint);
 

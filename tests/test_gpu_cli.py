@@ -120,6 +120,31 @@ def test_cpp_facade_members_match_oracle(pkg, oracle_mod, tmp_path):
         ph = np.zeros(3, np.float32)
         O.lib().or_phong_shade(orc.handle, origin.ctypes.data, hit.ctypes.data, int(face[0]), lights.ctypes.data, 2, ph.ctypes.data)
         assert np.allclose(f32(out["phong"]), ph, rtol=2e-6, atol=1e-7)
+    # headless debug ray: every level is a traceRay from the previous hit point along the mirror direction
+    dbg = out["debug_ray"]
+    assert dbg and dbg[0]["level"] == 0 and dbg[0]["face"] == int(face[0])
+    for k, lv in enumerate(dbg):
+        o_k, d_k = f32(lv["origin"]), f32(lv["direction"])
+        e_rgb = np.zeros(3, np.float32); e_face = np.zeros(1, np.int32); e_t = np.zeros(1, np.float32)
+        # (the facade lowers the depth cap by the level it starts at, like Flyscene::traceRay's level argument)
+        orc_k = O.Oracle(O.BakedScene(*arrs), area=1, point=0, max_depth=max(0, 2 - k), grid=(5, 5))
+        O.lib().or_trace_ray(orc_k.handle, o_k.ctypes.data, d_k.ctypes.data, 0, lights.ctypes.data, 2, e_rgb.ctypes.data,
+                             e_face.ctypes.data, e_t.ctypes.data)
+        assert lv["face"] == int(e_face[0]), (k, lv)
+        if lv["face"] < 0:
+            assert k == len(dbg) - 1
+            break
+        assert np.float32(lv["t"]) == e_t[0]
+        assert np.allclose(f32(lv["colour"]), e_rgb, rtol=2e-6, atol=1e-7)
+        hit_k = (o_k + e_t[0] * d_k).astype(np.float32)
+        vis_k = np.zeros(2, np.uint8)
+        O.lib().or_light_strikes(orc_k.handle, hit_k.ctypes.data, lights.ctypes.data, 2, vis_k.ctypes.data)
+        assert lv["visible"] == [int(vis_k[0]), int(vis_k[1])]
+        if k + 1 < len(dbg):  # next level starts at this hit point along the mirror direction
+            nrm = arrs[1][lv["face"]].astype(np.float32)
+            dn = np.float32(d_k[0] * nrm[0] + np.float32(d_k[1] * nrm[1] + d_k[2] * nrm[2]))
+            refl = (d_k - (np.float32(2) * dn) * nrm).astype(np.float32)
+            assert (f32(dbg[k + 1]["origin"]) == hit_k).all() and (f32(dbg[k + 1]["direction"]) == refl).all()
     assert out["n_samples"] == 25
     assert np.allclose(out["sample0"], (-0.0700000003, 0.114999995, 1), atol=1e-8)
     assert np.allclose(out["sample24"], (-0.629999995, 1.03499997, 1), atol=1e-8)
