@@ -245,3 +245,27 @@ def test_bvh_builder_invariants_host_only(pkg):
         bad = cases["mixed sizes"].copy()
         bad[7, 4] = np.nan
         capi.bvh_check(bad)
+
+
+def test_adaptive_band_height_partitions_every_frame(pkg):
+    """bench.band_rows_for: every rank gets ~8 bands; whatever it returns, the ranks' row maps must tile the
+    image exactly once (rt_local_row_map / rt_local_rows are host-only)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    capi = pkg.capi
+    for H in (1, 7, 36, 1000, 1080, 2160, 4320):
+        for world in (1, 2, 3, 4, 8):
+            B = bench.band_rows_for(H, world)
+            assert B >= 8 and B % 8 == 0
+            rows = []
+            for r in range(world):
+                p = capi.make_params(64, H, band_rows=B, band_rank=r, band_world=world)
+                rows.append(capi.local_row_map(p))
+            allrows = np.sort(np.concatenate(rows))
+            assert (allrows == np.arange(H)).all(), (H, world, B)
+            if H >= 1080 and world > 1:
+                sizes = [len(x) for x in rows]
+                assert max(sizes) - min(sizes) <= B
+                assert 4 <= -(-H // B) // world <= 9  # about 8 bands per rank
