@@ -570,11 +570,15 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload, {}).get(kname)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "kernel": kname,
+                # measured DRAM bytes of that launch over its duration: the HBM bandwidth the kernel really draws
+                "dram_gbs": (traffic / (dom_ms * 1e-3) / 1e9) if traffic else None,
+                "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "achieved = cache-level ALGORITHMIC bytes (32 B per ray-AABB test, 48 B per ray-triangle test, "
                         "SURVEY.md 8d) of the dominant kernel / its CUDA-event duration; traffic = measured DRAM bytes of "
-                        "that kernel (ncu --set full, profiles/r01_traffic.json): the working set is served by L1/L2, "
-                        "the path is SM-issue bound, see sm_issue",
+                        "that kernel (ncu --set full, profiles/r01_traffic.json) and dram_gbs / dram_frac what that is per second "
+                        "and against the HBM peak: the working set is served by L1/L2, the path is SM-issue / load-latency "
+                        "bound, see sm_issue",
                 "sm_issue": {"achieved_thread_instr_per_s": w_alg / (frame_ms_1gpu * 1e-3),
                              "peak_thread_instr_per_s": issue_peak, "frac": w_alg / (frame_ms_1gpu * 1e-3) / issue_peak,
                              "model": "16*N_box + 40*N_tri + 120*N_samples over the whole frame (rank 0's share)"}}
