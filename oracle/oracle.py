@@ -232,8 +232,9 @@ def load_render_dump(path: str) -> RefRender:
 def run_ref(scene_obj: str, out: str, w: int, h: int, area: int = 0, point: int = 1, stride: int = 1,
             offx: int = 0, offy: int = 0, threads: int = 0, dump_scene: str | None = None,
             lights=None, cam_rot=None, cam_trans=None, primary_only=False, max_depth=None, grid=None,
-            timeout=3600) -> str:
-    """Run the reference (oracle/_ref/ref_oracle[_patched]) headless; returns its stdout (JSON line)."""
+            timeout=3600, capture=True) -> str:
+    """Run the reference (oracle/_ref/ref_oracle[_patched]) headless; returns its stdout (JSON line).
+    capture=False (timing runs) skips the driver's untimed second pass that records primary face id / t."""
     patched = max_depth is not None or grid is not None
     cmd = [REF_BIN_PATCHED if patched else REF_BIN, "--scene", scene_obj, "--w", str(w), "--h", str(h),
            "--area", str(area), "--point", str(point), "--stride", str(stride), "--offx", str(offx),
@@ -250,6 +251,8 @@ def run_ref(scene_obj: str, out: str, w: int, h: int, area: int = 0, point: int 
         cmd += ["--cam-trans"] + [repr(float(c)) for c in cam_trans]
     if primary_only:
         cmd += ["--primary-only"]
+    if not capture:
+        cmd += ["--no-capture"]
     if max_depth is not None:
         cmd += ["--max-depth", str(max_depth)]
     if grid is not None:
@@ -258,6 +261,23 @@ def run_ref(scene_obj: str, out: str, w: int, h: int, area: int = 0, point: int 
     if r.returncode != 0:
         raise RuntimeError(f"ref_oracle failed rc={r.returncode}: {r.stderr[-2000:]}")
     return r.stdout
+
+
+def run_ref_raytrace_scene(scene_obj: str, size: int, area: int = 0, point: int = 1, timeout=3600):
+    """The reference's OWN frame driver, Flyscene::raytraceScene() (src/flyscene.cpp:519-648): its pixel
+    pre-pass, its ThreadPool (hardware_concurrency() - 1 workers), traceRay per pixel and the ASCII result.ppm
+    write, timed by its own clock (the "ELAPSED TIME:" line it prints, :646).  Square images only (the
+    reference indexes pixel_data[x][y] on a [H][W] array).  Returns (elapsed_s, threads, path of result.ppm)."""
+    import re
+    cmd = [REF_BIN, "--scene", scene_obj, "--w", str(size), "--h", str(size), "--area", str(area), "--point", str(point),
+           "--mode", "rts"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    m = re.search(r"ELAPSED TIME:([0-9.eE+-]+)", r.stdout)
+    if m is None:
+        raise RuntimeError(f"raytraceScene printed no ELAPSED TIME (rc={r.returncode}): {r.stderr[-1000:]}")
+    thr = re.search(r"Threads utilized:\s+(\d+)", r.stdout)
+    cwd = re.search(r"scratch_cwd (\S+)", r.stderr)
+    return float(m.group(1)), int(thr.group(1)) if thr else 0, os.path.join(cwd.group(1), "result.ppm") if cwd else None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -574,7 +574,17 @@ extern "C" int rt_bvh_check(const RtSceneDesc *desc, int32_t leaf_size, int64_t 
     for (int c = 0; c < 2; ++c) {
       int32_t code;
       memcpy(&code, &pn.q[12 + c], 4);
-      if (code == rt::kEmptyLeaf) continue;
+      if (code == rt::kEmptyLeaf) {
+        // only the root of an EMPTY scene may have unused slots: the device's slab test would accept the
+        // inverted box of an empty slot (see bvh_builder.cpp)
+        if (T > 0) return fail(RT_ERR_INVALID, "node %d has an empty child slot", it.node);
+        continue;
+      }
+      if (c == 1 && T == 1) {  // single primitive: both slots name the same leaf
+        int32_t code0;
+        memcpy(&code0, &pn.q[12], 4);
+        if (code == code0) continue;
+      }
       const float mn[3] = {pn.q[4 * c + 0], pn.q[4 * c + 2], pn.q[8 + 2 * c]};
       const float mx[3] = {pn.q[4 * c + 1], pn.q[4 * c + 3], pn.q[9 + 2 * c]};
       for (int a = 0; a < 3; ++a)

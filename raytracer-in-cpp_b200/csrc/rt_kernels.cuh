@@ -169,8 +169,10 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
           tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || sc.n_spheres > 0;
         }
         // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
+        // (the reference divides by (o + d) - o, which differs from d by up to ulp(|o|) / |d|: more than the
+        // margin of the decisive test for a slow, far-away secondary ray, so that test gets its own reciprocal)
         const V3 dest = add(o, d);
-        tri_enabled = tri_enabled && ref_box_intersect_quick(sc.root_min, sc.root_max, o, dest, rdir);
+        tri_enabled = tri_enabled && ref_box_intersect_quick(sc.root_min, sc.root_max, o, dest, recip_dir(sub(dest, o)));
         if (tri_enabled || sc.n_spheres > 0) {  // else: missed the root box, BACKGROUND
           tr.init(o, d, dest, tri_enabled, rdir);
           active = true;
@@ -320,9 +322,11 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
     bool active = false, have = false;
     uint8_t visible = 0;
     if (slot < n_slots) {
-      const float4 hp = lv.hit_p[slot];
-      const V3 hit = mk(hp);
-      const int iw = __float_as_int(hp.w);
+      const float2 hxy = *reinterpret_cast<const float2 *>(lv.hit_p + slot);
+      const V3 hit = mk(hxy.x, hxy.y, reinterpret_cast<const float *>(lv.hit_p + slot)[2]);
+      // the flag word may be set concurrently by the gate unit of this hit (atomicOr below): read it with a
+      // relaxed volatile load of its own instead of as part of the float4
+      const int iw = *reinterpret_cast<volatile const int *>(reinterpret_cast<const int *>(lv.hit_p + slot) + 3);
       V3 src;
       if (iw & 1) {
         // mirror child: its light list is the single point it inherited (the parent's hit point)
@@ -366,8 +370,8 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
       if (j == 0u && S > 0 && visible == 0) {
         // gate ray of light 0 occluded: if it is the hit's only light, flag the hit
         int *w = reinterpret_cast<int *>(lv.hit_p + slot) + 3;
-        const int iw = *w;
-        if ((iw & 1) || fp.n_lights == 1) *w = iw | RT_HIT_DARK;
+        const int iw = *reinterpret_cast<volatile int *>(w);
+        if ((iw & 1) || fp.n_lights == 1) atomicOr(w, RT_HIT_DARK);
       }
     }
   }

@@ -229,12 +229,29 @@ BvhBuildResult build_bvh(const std::vector<Aabb> &prim_boxes, const std::vector<
 
   Emitter em{b, kind, out};
   if (b.nodes[root].left < 0) {
-    // the whole scene fits one leaf: wrap it in a pair node with an empty sibling
+    // The whole scene fits one leaf, but the root is a PAIR node.  An empty sibling slot is not an option:
+    // the device's min/max slab test is symmetric, so the inverted (+inf, -inf) box of an empty slot passes
+    // it, and the traversal would take the empty code for the bottom-of-stack sentinel and stop before the
+    // real leaf.  Two primitives or more: split the leaf in two halves (median).  A single primitive:
+    // both slots name the same leaf (testing it twice gives the same hit).
     PairNode pn{};
-    const int32_t c0 = em.code_of(root, 1);
-    Emitter::set_child(pn, 0, b.nodes[root].box, c0);
-    Emitter::set_child(pn, 1, empty, kEmptyLeaf);
-    out.nodes.push_back(pn);
+    if (N >= 2) {
+      BuildNode &rn = b.nodes[root];
+      Box cb;
+      for (int32_t k = 0; k < (int32_t)N; ++k) cb.grow_pt(&b.cent[3 * (size_t)b.idx[k]]);
+      const int32_t mid = b.median_partition(0, (int32_t)N, cb);
+      const int32_t l = b.alloc(), r = b.alloc();
+      rn.left = l; rn.right = r;
+      b.build(l, 0, mid, 1);
+      b.build(r, mid, (int32_t)N, 1);
+      out.prim_order = b.idx;
+      em.code_of(root, 0);
+    } else {
+      const int32_t c0 = em.code_of(root, 1);
+      Emitter::set_child(pn, 0, b.nodes[root].box, c0);
+      Emitter::set_child(pn, 1, b.nodes[root].box, c0);
+      out.nodes.push_back(pn);
+    }
   } else {
     em.code_of(root, 0);
   }

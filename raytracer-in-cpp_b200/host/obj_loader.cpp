@@ -151,13 +151,24 @@ BakedMesh load_obj(const std::string &obj_path, bool normalize) {
         char *q;
         long id = std::strtol(c, &q, 10);
         if (q == c) break;
-        groups.back().push_back((uint32_t)(id - 1));
+        // OBJ ids are 1-based; a negative id counts back from the vertices read so far.  Anything that does
+        // not name an existing vertex would index past obj_verts / normals below: reject the file instead
+        // (the reference reads out of bounds there, tucano/utils/objimporter.hpp:196-214).
+        const long nv_here = (long)(m.obj_verts.size() / 3);
+        const long zero_based = id < 0 ? nv_here + id : id - 1;
+        if (id == 0 || zero_based < 0) throw std::runtime_error("face index " + std::to_string(id) + " out of range in " + obj_path);
+        groups.back().push_back((uint32_t)zero_based);
         c = q;
         while (c < e && *c != ' ' && *c != '\t' && *c != '\r') ++c;  // skip /vt/vn
       }
     }
   }
   const size_t NV = m.obj_verts.size() / 3;
+  for (const auto &g : groups)
+    for (uint32_t id : g)
+      if ((size_t)id >= NV)
+        throw std::runtime_error("face index " + std::to_string((unsigned long)id + 1) + " exceeds the " + std::to_string(NV) +
+                                 " vertices of " + obj_path);
   auto V = [&](uint32_t i) { return Vec3f(&m.obj_verts[3 * (size_t)i]); };
 
   // ---- vertex normals: list = file vn's followed by NV zero vectors; face normals are

@@ -83,6 +83,8 @@ SCENE_OF = {
 # cases whose scene is regenerated from the deterministic generators and loaded by the product loader
 GENERATED = {
     "hf224_point_3840x2160_s24": ("write_heightfield", (224,)),
+    "hf224_area_d5_g4_3840x2160_s24": ("write_heightfield", (224,)),
+    "hf224m_area_d5_g4_3840x2160_s48": ("write_heightfield", (224, 1234, 4)),
     "hf707_point_1920x1080_s20": ("write_heightfield", (707,)),
     "hf707_point_7680x4320_s80": ("write_heightfield", (707,)),
 }

@@ -57,6 +57,13 @@ CASES = {
                                       stride=20, keep_scene=False),
     "hf707_point_7680x4320_s80": dict(scene=("gen", "write_heightfield", (707,)), w=7680, h=4320, area=0, point=1,
                                       stride=80, keep_scene=False),
+    # BASELINE configs[3] as bench.py runs it, minus the analytic spheres (which the reference does not have):
+    # 100 352 triangles, 3840x2160, 4x4 area light, depth cap 5 -- and the same with a mirror (illum 4) field so
+    # that the depth-5 recursion is actually exercised on 100 k triangles
+    "hf224_area_d5_g4_3840x2160_s24": dict(scene=("gen", "write_heightfield", (224,)), w=3840, h=2160, area=1, point=0,
+                                           stride=24, max_depth=5, grid=(4, 4), keep_scene=False),
+    "hf224m_area_d5_g4_3840x2160_s48": dict(scene=("gen", "write_heightfield", (224, 1234, 4)), w=3840, h=2160, area=1,
+                                            point=0, stride=48, max_depth=5, grid=(4, 4), keep_scene=False),
     "cube_area_d3_g4_1920x1080_s9": dict(scene=("ref", "cube.obj"), w=1920, h=1080, area=1, point=0, stride=9,
                                          max_depth=3, grid=(4, 4), keep_scene=False),
 }

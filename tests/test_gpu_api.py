@@ -392,3 +392,45 @@ def test_shared_reciprocal_division_is_ieee_exact(pkg):
     capi.init(0)
     for seed, exp_range in [(1, 2), (2, 20), (3, 59), (4, 70), (5, 0), (6, 126)]:
         assert capi.selftest_div3(1 << 31, seed, exp_range) == 0, (seed, exp_range)
+
+
+@pytest.mark.parametrize("n_tri,leaf", [(1, 2), (2, 2), (2, 1), (3, 16), (12, 16)])
+def test_scenes_that_fit_one_leaf(n_tri, leaf, pkg, oracle_mod):
+    """A scene with no more primitives than the leaf size used to get a root pair node with an empty slot,
+    whose inverted box passes the symmetric slab test: every ray then stopped at the bottom-of-stack
+    sentinel before reaching the only leaf and the frame came out all BACKGROUND.  Rendered against the
+    oracle: one triangle, two triangles, and the bundled cube with leaf_size 16 (12 triangles, one leaf)."""
+    O = oracle_mod
+    capi = pkg.capi
+    capi.init(0)
+    if n_tri == 12:
+        g = load_golden("cube_point_1000")
+        arrs = [g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"]]
+    else:
+        v = np.array([[[-0.8, -0.6, 0.0], [0.7, -0.5, 0.1], [0.0, 0.8, -0.1]],
+                      [[-0.5, 0.2, 0.4], [0.6, 0.3, 0.5], [0.1, -0.7, 0.45]],
+                      [[-0.9, 0.7, -0.3], [-0.2, 0.9, -0.2], [-0.6, 0.1, -0.35]]], np.float32)[:n_tri]
+        e0, e1 = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]
+        fn = np.cross(e0, e1)
+        fn = (fn / np.linalg.norm(fn, axis=1, keepdims=True)).astype(np.float32)
+        vn = np.repeat(fn[:, None, :], 3, axis=1).copy()
+        arrs = [v, fn, vn, np.zeros(n_tri, np.int32), np.array([[0.7, 0.6, 0.5, 1, 1, 1, 20, 0, 2]], np.float32)]
+    capi.set_option("leaf_size", leaf)
+    try:
+        scene = capi.Scene(*arrs)
+    finally:
+        capi.set_option("leaf_size", 2)
+    W, H = 200, 150
+    lights_np = np.array([[-1, 1, 1.5]], np.float32)
+    fr = scene.render(capi.default_camera(W, H), capi.Lights(lights_np), capi.make_params(W, H, 1, 0, 2, (3, 3)))
+    orc = O.Oracle(O.BakedScene(*arrs), area=1, point=0, max_depth=2, grid=(3, 3))
+    cam = O.Oracle.camera((0, 0, 2), np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 2]], np.float32), (0, 0, W, H), 60.0,
+                          np.float32(W) / np.float32(H))
+    pxy, rgb, face, t, rgb8 = orc.render(cam, lights_np, W, H, stride=1, threads=4)
+    px, py = pxy[:, 0], pxy[:, 1]
+    assert (face >= 0).sum() > 1000, "the primitives should be visible"
+    assert (fr.face[py, px] == face).all()
+    assert (fr.t[py, px].view(np.uint32) == t.view(np.uint32)).all()
+    err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - np.clip(O.quantize(rgb), 0, 255)).max(-1)
+    assert err.max() <= 1 and (err == 0).mean() > 0.999
+    scene.close()

@@ -71,6 +71,27 @@ def test_loader_errors(pkg, tmp_path):
     assert pkg.capi.Mesh(str(e2)).arrays()[0].shape[0] == 0
 
 
+def test_loader_rejects_face_indices_outside_the_vertex_list(pkg, tmp_path):
+    """OBJ ids that do not name an existing vertex used to index past the vertex / normal arrays (heap
+    corruption); they must come back as RT_ERR_IO.  Negative ids are relative to the vertices read so far."""
+    capi = pkg.capi
+    tri = "v 0 0 0\nv 1 0 0\nv 0 1 0\n"
+    for body in ("f 1 2 4\n", "f 0 1 2\n", "f 1 2 -4\n", "f 1 2 99999999\n"):
+        p = tmp_path / "bad.obj"
+        p.write_text(tri + body)
+        with pytest.raises(capi.RtError) as e:
+            capi.Mesh(str(p))
+        assert e.value.code == -4 and "face index" in str(e.value)
+    # a relative index resolves against the vertex count AT THAT LINE, not the final one
+    p = tmp_path / "rel.obj"
+    p.write_text(tri + "f -3 -2 -1\nv 5 5 5\nf 1 2 -1\n")
+    a = capi.Mesh(str(p), ).arrays()
+    q = tmp_path / "abs.obj"
+    q.write_text(tri + "f 1 2 3\nv 5 5 5\nf 1 2 4\n")
+    b = capi.Mesh(str(q)).arrays()
+    assert a[0].shape == (2, 3, 3) and _bits(a[0], b[0]) == 0 and _bits(a[1], b[1]) == 0 and _bits(a[2], b[2]) == 0
+
+
 def test_library_exports_every_declared_symbol(pkg):
     hdr = open(os.path.join(ROOT, "include", "rt_api.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
@@ -241,6 +262,14 @@ def test_bvh_builder_invariants_host_only(pkg):
             assert r["refs"] == v.shape[0], name
             assert r["max_leaf"] <= leaf or v.shape[0] == 0, (name, r)
             assert r["depth"] <= 60, (name, r)
+    # scenes that fit one leaf: the root pair must not keep an empty slot (its inverted box passes the
+    # device's slab test); rt_bvh_check refuses such a tree
+    for n in (1, 2, 3, 12):
+        v = rng.uniform(-1, 1, (n, 9)).astype(np.float32)
+        for leaf in (1, 2, 16):
+            r = capi.bvh_check(v, leaf)
+            assert r["refs"] == n and r["nodes"] >= 1
+            assert r["leaves"] >= min(n, 2), (n, leaf, r)
     with pytest.raises(capi.RtError, match="non-finite"):
         bad = cases["mixed sizes"].copy()
         bad[7, 4] = np.nan

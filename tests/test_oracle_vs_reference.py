@@ -11,7 +11,7 @@ import pytest
 
 from conftest import GENERATED, SCENE_OF, case_params, load_golden, scene_arrays
 
-FAST_CASES = list(SCENE_OF) + ["hf224_point_3840x2160_s24"]
+FAST_CASES = list(SCENE_OF) + ["hf224_point_3840x2160_s24", "hf224_area_d5_g4_3840x2160_s24", "hf224m_area_d5_g4_3840x2160_s48"]
 
 
 def _oracle_for(case, pkg, O, scene_dir, **kw):
