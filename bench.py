@@ -95,12 +95,6 @@ def workload_obj(wl):
     return path
 
 
-def workload_arrays_host(wl):
-    """Same as workload_arrays; named separately to make clear that only the host-side loader of the
-    C-ABI library is used (no GPU needed)."""
-    return workload_arrays(wl)
-
-
 def workload_arrays(wl):
     """Baked scene arrays (+ optional spheres) for a workload."""
     capi = pkg().capi
@@ -188,7 +182,8 @@ def reference_sample(wl, stride, threads=0):
         out = os.path.join(tempfile.gettempdir(), f"rt_ref_sample_{os.getpid()}.bin")
         O.run_ref(obj, out, w, h, wl["area"], wl["point"], stride, threads=threads,
                   max_depth=(wl["max_depth"] if patched and wl["max_depth"] >= 0 else (1 << 30 if patched else None)),
-                  grid=(tuple(wl["grid"]) if patched else None))
+                  grid=(tuple(wl["grid"]) if patched else None),
+                  capture=False)  # timed: only the reference's own per-pixel work (no face / t capture pass)
         r = O.load_render_dump(out)
         os.remove(out)
         return r.render_s, len(r.face), "reference", r.threads
@@ -204,11 +199,29 @@ def reference_sample(wl, stride, threads=0):
     return time.perf_counter() - t0, len(pxy), "port", nthr
 
 
+def reference_raytrace_scene_c1():
+    """BASELINE configs[0] through the reference's OWN frame driver: Flyscene::raytraceScene() on the bundled cube at
+    the reference resolution (1000x1000, point light) -- pixel pre-pass, ThreadPool of hardware_concurrency()-1
+    workers, traceRay per pixel, ASCII result.ppm -- timed by the reference's own clock (its "ELAPSED TIME" line,
+    src/flyscene.cpp:521,642-647).  The reference cannot run this driver on non-square images, so
+    the 1080p workloads are timed through the direct traceRay loop instead; this leg shows what its own driver adds."""
+    from oracle import oracle as O
+    if not O.have_ref():
+        return None
+    try:
+        s, thr, _ = O.run_ref_raytrace_scene(os.path.join(O.REF_SCENES, "cube.obj"), 1000, 0, 1)
+    except Exception as ex:
+        return {"unavailable": str(ex)[:200]}
+    rays = 1000000 + 2 * 494209  # App. A.8: 494 209 hit pixels x (merged gate/sample ray + mirror child) + primaries
+    return {"workload": WORKLOADS["c1"]["desc"], "call": "Flyscene::raytraceScene() (reference frame driver incl. result.ppm)",
+            "elapsed_s": s, "threads": thr, "value": rays / s / 1e6, "unit": "Mrays/s", "rays_per_frame": rays}
+
+
 def census_rays(wl, stride):
     """Rays (reference census, SURVEY.md App. A.8, shadow gate+sample merged in point mode) that the
     sampled pixels generate, counted by the C port on the same pixels.  Not timed."""
     from oracle import oracle as O
-    arrs, spheres, sphere_mat = workload_arrays_host(wl)
+    arrs, spheres, sphere_mat = workload_arrays(wl)
     orc = O.Oracle(O.BakedScene(*arrs, spheres=spheres, sphere_mat=sphere_mat), area=wl["area"], point=wl["point"],
                    max_depth=wl["max_depth"], grid=wl["grid"])
     w, h = wl["w"], wl["h"]
@@ -250,8 +263,37 @@ def run_reference_arm(args, wl, rays_per_pixel):
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": thr, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_frame_extrapolated": 1e3 * total / len(secs) * (wl["w"] * wl["h"]) / max(1, pix),
+        "reference_frame_driver_c1": reference_raytrace_scene_c1(),
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources of the library: ties a committed ncu capture to the build it was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "raytracer-in-cpp_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_metrics_for(workload, kernel):
+    """Measured per-launch counters of `kernel` on `workload` (dram bytes, executed thread-instructions) from the
+    committed ncu capture -- only if that capture was taken on the kernel sources of THIS build."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    if d.get("source_hash") != kernel_source_hash():
+        return None
+    m = d.get("workloads", {}).get(workload, {}).get(kernel)
+    if m:
+        m = dict(m)
+        m["source"] = "ncu --set full capture on this build (profiles/r02_ncu_metrics.json, source hash %s)" % d["source_hash"]
+    return m
 
 
 # ----------------------------------------------------------------------------------------------
@@ -307,7 +349,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="repeat the timed K-step block until this many seconds of frames have been timed")
     ap.add_argument("--band-rows", type=int, default=0, help="multi-GPU band height; 0 = band_rows_for(H, world)")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
+                    help="rt_set_option before the scene is created (developer A/B runs), e.g. --opt fused_frame=0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -346,6 +392,9 @@ def main():
         dist.barrier()
     capi = pkg().capi
     capi.init(local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        capi.set_option(k, int(v))
 
     arrs, spheres, sphere_mat = workload_arrays(wl)
     scene = capi.Scene(*arrs, None, spheres, sphere_mat)
@@ -413,38 +462,54 @@ def main():
         dist.all_reduce(rays_t)
     rays_total, n_primary, n_shadow, n_secondary = [float(x) for x in rays_t.tolist()]
 
-    # ---- timed: exactly K steps, CUDA events on the launch stream, L2 flushed between steps ----
+    # ---- timed: blocks of exactly K steps, CUDA events on the launch stream, L2 flushed between steps ----
+    # One block = the K steps the contract asks for (barrier + synchronize on both sides, max over ranks).  A 20-step
+    # block of a 0.3 ms frame is a 7 ms measurement: too short for the clock sampler to see and with unknown noise.
+    # So the block is REPEATED until at least `--min-seconds` of frames have been timed (at most 200 blocks); `value`
+    # and `ms_per_step` come from the MEDIAN block, the spread over blocks is reported beside them.
     def timed(fn):
         for _ in range(args.warmup):
             fn()
         torch.cuda.synchronize()
         sampler_ = ClockSampler(local_rank)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
         sampler_.start()
-        w0 = time.perf_counter()
-        for a, b in evs:
-            flush.zero_()
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        wall_ = time.perf_counter() - w0
+        blocks, wall_total, steps_total = [], 0.0, 0
+        while True:
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for a, b in evs:
+                flush.zero_()
+                a.record()
+                fn()
+                b.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            wall_total += time.perf_counter() - w0
+            ms_t = torch.tensor([float(sum(a.elapsed_time(b) for a, b in evs))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+            blocks.append(float(ms_t.item()))
+            steps_total += args.steps
+            # every rank must take the same decision: it is taken on the all-reduced block times
+            if sum(blocks) * 1e-3 >= args.min_seconds or len(blocks) >= 200:
+                break
         clocks_ = sampler_.stop()
-        ms_t = torch.tensor([float(sum(a.elapsed_time(b) for a, b in evs))], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-        return float(ms_t.item()), wall_, clocks_
+        per_step = np.array(blocks) / args.steps
+        spread_ = {"blocks": len(blocks), "steps_timed": steps_total, "ms_per_step_median": float(np.median(per_step)),
+                   "ms_per_step_min": float(per_step.min()), "ms_per_step_max": float(per_step.max()),
+                   "ms_per_step_p10": float(np.percentile(per_step, 10)), "ms_per_step_p90": float(np.percentile(per_step, 90)),
+                   "rel_spread_p10_p90": float((np.percentile(per_step, 90) - np.percentile(per_step, 10)) / np.median(per_step))}
+        return float(np.median(blocks)), wall_total, clocks_, spread_
 
     kernel_ms = {"trace": 0.0, "shadow": 0.0, "shade": 0.0}
-    ms_total, wall, clocks = timed(step)
+    ms_total, wall, clocks, spread = timed(step)
     nccl_line = None
     if step_peer is not None:
-        ms_peer, wall_peer, clocks_peer = timed(step_peer)
+        ms_peer, wall_peer, clocks_peer, spread_peer = timed(step_peer)
         nccl_line = {"value": rays_total * args.steps / (ms_total * 1e-3) / 1e6, "ms_per_step": ms_total / args.steps,
                      "note": "baseline: bands gathered to rank 0 with torch.distributed.gather (NCCL) + scatter"}
         # correctness of the fused path: rank 0's peer-assembled frame == the NCCL-gathered frame
@@ -452,20 +517,31 @@ def main():
         torch.cuda.synchronize(); dist.barrier()
         if rank == 0:
             match = bool((torch.from_numpy(shared.to_host()).to(dev) == gather.frame).all().item())
-        ms_total, wall, clocks = ms_peer, wall_peer, clocks_peer
+        ms_total, wall, clocks, spread = ms_peer, wall_peer, clocks_peer, spread_peer
         nccl_line["frames_match"] = match
     ms_per_step = ms_total / args.steps
     value = rays_total * args.steps / (ms_total * 1e-3) / 1e6
 
     # ---- per-kernel durations (live, CUDA events inside the library on the same stream) ----
+    # Wavefront frames: one CUDA-event span per kernel family.  Fused frames (RtStats.fused): ONE kernel, timed as a
+    # whole ("frame"); its split into trace / shadow / shade comes from the stats frame above, where the kernel
+    # counted the warp-cycles of its phases.
     reps = min(10, args.steps)
+    fused = bool(stats.get("fused"))
+    if fused:
+        kernel_ms = {"frame": 0.0}
     for _ in range(reps):
         flush.zero_()
         s2 = capi.RtStats()
         scene.render_device(cam, lights, params, local.data_ptr(), stream=stream, stats=s2)
-        kernel_ms["trace"] += s2.ms_trace / reps
-        kernel_ms["shadow"] += s2.ms_shadow / reps
-        kernel_ms["shade"] += s2.ms_shade / reps
+        if fused:
+            kernel_ms["frame"] += s2.ms_total / reps
+        else:
+            kernel_ms["trace"] += s2.ms_trace / reps
+            kernel_ms["shadow"] += s2.ms_shadow / reps
+            kernel_ms["shade"] += s2.ms_shade / reps
+    if fused and stats["ms_total"] > 0:
+        kernel_ms["phase_share"] = {k: stats["ms_" + k] / stats["ms_total"] for k in ("trace", "shadow", "shade")}
 
     # ---- e2e: the user-facing blocking call with pinned HOST buffers, copies inside the timed region ----
     # N = 1: rt_render() (H2D of camera/lights/params, render, D2H of the packed frame).
@@ -537,51 +613,52 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ----
+    # ---- roofline of the dominant kernel (SURVEY.md 8d) ----
+    # The path is SM-issue bound, not HBM bound: the algorithmic work of a launch is
+    #     W_alg = 16 * ray-AABB tests + 40 * ray-triangle tests + 120 * shaded light samples   [thread-instructions]
+    # (counted by a stats build of the same kernels on the same frame) and the peak is one instruction per lane,
+    # scheduler and cycle: 148 SMs x 4 schedulers x 32 lanes x f_SM.  `frac` is that of the dominant kernel over its
+    # own CUDA-event duration, `frac_frame` of the whole frame over ms_per_step.  The HBM side is reported beside it
+    # from MEASURED DRAM bytes (ncu) when the committed capture was taken on exactly these kernel sources.
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    dom = max(kernel_ms, key=kernel_ms.get)
-    if dom == "shadow":
-        nb, nt = stats["box_tests_shadow"], stats["tri_tests_shadow"]
-        out_bytes = stats["rays_shadow"]  # one visibility byte per shadow job
-    elif dom == "trace":
-        nb, nt = stats["box_tests"], stats["tri_tests"]
-        out_bytes = 8 * (stats["rays_primary"] + stats["rays_secondary"])
+    sm_mhz = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965)
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    issue_peak = n_sm * 4 * 32 * sm_mhz * 1e6
+    w_kernel = {"trace": 16.0 * stats["box_tests"] + 40.0 * stats["tri_tests"],
+                "shadow": 16.0 * stats["box_tests_shadow"] + 40.0 * stats["tri_tests_shadow"],
+                "shade": 120.0 * stats["shade_samples"]}
+    w_frame = sum(w_kernel.values())
+    if fused:
+        dom, kname, w_dom, dom_ms = "frame", "k_frame", w_frame, max(kernel_ms["frame"], 1e-6)
     else:
-        nb, nt = 0, 0
-        out_bytes = 4 * stats["pixels"]
-    # 32 B per ray-AABB test (one child box of a pair node), 48 B per ray-triangle test
-    alg_bytes = 32.0 * nb + 48.0 * nt + out_bytes
-    dom_ms = max(kernel_ms[dom], 1e-6)
-    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    sm_mhz = clocks.get("sm_max_mhz") or 1965
-    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6
-    w_alg = 16.0 * (stats["box_tests"] + stats["box_tests_shadow"]) + 40.0 * (stats["tri_tests"] + stats["tri_tests_shadow"]) \
-        + 120.0 * stats["shade_samples"]
-    frame_ms_1gpu = ms_per_step
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    kname = {"trace": "k_trace_nearest", "shadow": "k_shadow", "shade": "k_shade"}[dom]
-    if world == 1 and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get(kname)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "kernel": kname,
-                # measured DRAM bytes of that launch over its duration: the HBM bandwidth the kernel really draws
-                "dram_gbs": (traffic / (dom_ms * 1e-3) / 1e9) if traffic else None,
-                "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
-                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "achieved = cache-level ALGORITHMIC bytes (32 B per ray-AABB test, 48 B per ray-triangle test, "
-                        "SURVEY.md 8d) of the dominant kernel / its CUDA-event duration; traffic = measured DRAM bytes of "
-                        "that kernel (ncu --set full, profiles/r01_traffic.json) and dram_gbs / dram_frac what that is per second "
-                        "and against the HBM peak: the working set is served by L1/L2, the path is SM-issue / load-latency "
-                        "bound, see sm_issue",
-                "sm_issue": {"achieved_thread_instr_per_s": w_alg / (frame_ms_1gpu * 1e-3),
-                             "peak_thread_instr_per_s": issue_peak, "frac": w_alg / (frame_ms_1gpu * 1e-3) / issue_peak,
-                             "model": "16*N_box + 40*N_tri + 120*N_samples over the whole frame (rank 0's share)"}}
+        dom = max(("trace", "shadow", "shade"), key=lambda k: kernel_ms[k])
+        kname = {"trace": "k_trace_nearest", "shadow": "k_shadow", "shade": "k_shade"}[dom]
+        w_dom, dom_ms = w_kernel[dom], max(kernel_ms[dom], 1e-6)
+    achieved = w_dom / (dom_ms * 1e-3)
+    measured = ncu_metrics_for(args.workload, kname) if world == 1 else None
+    traffic = measured.get("dram_bytes") if measured else None
+    scene_bytes = int(info.get("device_bytes", 0))
+    roofline = {"bound": "sm_issue", "achieved": achieved, "peak": issue_peak, "unit": "thread-instr/s",
+                "frac": achieved / issue_peak, "frac_frame": w_frame / (ms_per_step * 1e-3) / issue_peak,
+                "kernel": kname, "kernel_ms": dom_ms, "algorithmic_thread_instr_per_launch": w_dom,
+                "algorithmic_thread_instr_per_frame": w_frame,
+                "model": "16 per ray-AABB test + 40 per ray-triangle test + 120 per shaded light sample (SURVEY.md 8d); "
+                         "peak = %d SMs x 4 schedulers x 32 lanes x %.0f MHz" % (n_sm, sm_mhz),
+                "executed_over_algorithmic": (measured["thread_inst_executed"] / w_dom) if measured and w_dom else None,
+                "traffic": traffic,
+                "hbm": {"bytes_per_launch_measured": traffic,
+                        "gbs": (traffic / (dom_ms * 1e-3) / 1e9) if traffic else None,
+                        "peak_gbs": hbm_peak, "peak_source": peak_src,
+                        "frac": (traffic / (dom_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                        "compulsory_bytes_per_frame": scene_bytes + 4 * W * H,
+                        "source": (measured or {}).get("source",
+                                                     "no ncu capture of these kernel sources is committed (profiles/r02_ncu_metrics.json "
+                                                     "is keyed by a hash of csrc/): not reported rather than replayed from an older build")}}
 
     json.dump({"rays_per_pixel": rays_total / (W * H)}, open(census_file, "w"))
 
@@ -610,14 +687,16 @@ def main():
                                    ("kernels store pixels into rank 0's framebuffer over NVLink peer memory (CUDA IPC), "
                                     "4-byte NCCL all-reduce as completion signal" if nccl_line else "NCCL gather to rank 0"))
                    if world > 1 else "1 GPU",
-                   "bvh": info},
+                   "bvh": info, "options": args.opt},
         "rays": {"per_frame": rays_total, "primary": n_primary, "shadow": n_shadow, "secondary": n_secondary,
                  "note": "gate and sample shadow rays are separate queries in area mode (as in the reference); "
                          "in point mode the identical gate/sample ray is traced and counted once"},
         "mpix_per_s": W * H * args.steps / (ms_total * 1e-3) / 1e6,
         "work": {k: stats[k] for k in ("box_tests", "tri_tests", "box_tests_shadow", "tri_tests_shadow", "shade_samples",
                                          "filter_checks", "filter_slow", "filter_rejects", "shadow_rays_traced")},
-        "kernel_ms": kernel_ms, "gpu_launches": int(stats["kernel_launches"] * args.steps),
+        "timing": spread,
+        "kernel_ms": kernel_ms, "frame_path": "fused (one persistent kernel)" if fused else "wavefront (CUDA graph of per-level kernels)",
+        "gpu_launches": int(stats["kernel_launches"] * args.steps),
         "clocks": clocks, "wall_s": wall, "nccl_gather_baseline": nccl_line, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

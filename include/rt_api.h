@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 2
+#define RT_API_VERSION 3
 #define RT_MAX_LIGHTS 25   /* bool visibleLights[25], src/flyscene.cpp:699,835 */
 #define RT_MAX_SAMPLES 25
 
@@ -135,6 +135,9 @@ typedef struct {
   /* any-hit queries the shadow kernel actually traced ("stats" option): it skips the sample rays of a hit
    * once that hit's gate result is known to be "no light visible", and may trace a few before it is */
   int64_t shadow_rays_traced;
+  /* 1: the frame ran as ONE persistent kernel (csrc/rt_frame.cuh); ms_trace / ms_shadow / ms_shade are then that
+   * kernel's duration split by the warp-cycles its phases took ("stats" option), not separate launches */
+  int32_t fused;
 } RtStats;
 
 typedef struct RtScene RtScene;   /* device-resident BVH + triangle soup + shading tables */
@@ -151,7 +154,11 @@ int rt_device_name(char *buf, size_t n);
 /* runtime knobs: "stats" (0/1 traversal counters), "leaf_size", "persistent_ctas_per_sm",
  * "reference_candidates" (default 1: scenes created afterwards filter BVH hits through the
  * reference's octree candidate sets so that the image matches the reference bit for bit; 0: plain
- * BVH = exact nearest hit over all faces), "graph_conditionals" (1, default: empty bounce levels are skipped inside the frame's CUDA graph) */
+ * BVH = exact nearest hit over all faces), "graph_conditionals" (1, default: empty bounce levels are skipped inside the frame's CUDA graph),
+ * "fused_frame" (the frame as one persistent kernel, csrc/rt_frame.cuh: 0 never, 1 whenever eligible, 2 = default:
+ *   for frames of at most "fused_max_kpixels" thousand rays (default 1200) and for unbounded depth; larger frames
+ *   take the per-level wavefront kernels of csrc/rt_kernels.cuh -- both paths give bit-identical frames),
+ * "continue_min_lanes" (fused frame: child rays stay in their warp when at least this many of its lanes spawned one; default 8) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);
 

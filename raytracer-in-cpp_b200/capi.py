@@ -61,7 +61,7 @@ class RtStats(C.Structure):
                 ("box_tests", C.c_int64), ("tri_tests", C.c_int64), ("shade_samples", C.c_int64),
                 ("box_tests_shadow", C.c_int64), ("tri_tests_shadow", C.c_int64),
                 ("filter_checks", C.c_int64), ("filter_slow", C.c_int64), ("filter_rejects", C.c_int64),
-                ("shadow_rays_traced", C.c_int64)]
+                ("shadow_rays_traced", C.c_int64), ("fused", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -22,6 +22,7 @@
 #include "../host/obj_loader.hpp"
 #include "../host/ref_octree.hpp"
 #include "rt_kernels.cuh"
+#include "rt_frame.cuh"
 
 using namespace rtd;
 
@@ -38,6 +39,10 @@ int g_opt_leaf = 2;  // measured best on the 100 k / 1 M-triangle scenes (leaf t
 int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
 int g_opt_ref_candidates = 1;
 int g_opt_graph_cond = 1;  // skip empty bounce levels inside the frame graph (conditional nodes)
+int g_opt_fused = 2;       // frame as ONE persistent kernel (rt_frame.cuh): 0 never (wavefront pipeline of rt_kernels.cuh),
+                           // 1 whenever the frame is eligible, 2 (default) when it is also small enough (below)
+int g_opt_fused_max_kpix = 1200;  // auto mode: frames of at most this many thousand rays take the fused kernel
+int g_opt_cont_min = 8;    // fused frame: child rays stay in the warp when at least this many lanes spawned one
 
 int fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -144,6 +149,9 @@ struct RtScene {
   cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
   int submit_seq = 0;
+  // fused frame kernel (rt_frame.cuh): deferred-ray slabs, chain records, counters
+  DevBuf fq_o, fq_d, fq_x, frec_a, frec_b, fcounts;
+  FusedCounts *h_fcounts = nullptr;  // pinned mirror
   // CUDA graph of the bounded-depth frame (memset + every kernel launch), replayed while its key matches
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<long long> graph_key;
@@ -196,6 +204,9 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "persistent_ctas_per_sm")) g_opt_ctas_per_sm = std::max(0, value);
   else if (!strcmp(key, "reference_candidates")) g_opt_ref_candidates = value ? 1 : 0;
   else if (!strcmp(key, "graph_conditionals")) g_opt_graph_cond = value ? 1 : 0;
+  else if (!strcmp(key, "fused_frame")) g_opt_fused = std::max(0, std::min(2, value));
+  else if (!strcmp(key, "fused_max_kpixels")) g_opt_fused_max_kpix = std::max(0, value);
+  else if (!strcmp(key, "continue_min_lanes")) g_opt_cont_min = std::max(1, std::min(33, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
 }
@@ -473,6 +484,7 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     return rc;
   }
   if (cudaMallocHost((void **)&sc->h_counts, sizeof(FrameCounts)) != cudaSuccess ||
+      cudaMallocHost((void **)&sc->h_fcounts, sizeof(FusedCounts)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) {
     rt_scene_destroy(sc);
     return fail(RT_ERR_CUDA, "cudaMallocHost failed");
@@ -507,6 +519,8 @@ extern "C" void rt_scene_destroy(RtScene *sc) {
   sc->out_rgba.release(); sc->out_face.release(); sc->out_t.release(); sc->out_rgbf.release();
   sc->in_a.release(); sc->in_b.release();
   if (sc->h_counts) cudaFreeHost(sc->h_counts);
+  sc->fq_o.release(); sc->fq_d.release(); sc->fq_x.release(); sc->frec_a.release(); sc->frec_b.release(); sc->fcounts.release();
+  if (sc->h_fcounts) cudaFreeHost(sc->h_fcounts);
   delete sc;
 }
 
@@ -947,6 +961,122 @@ int build_conditional_frame_graph(RtScene *sc, const FramePlan &pl, cudaGraphExe
   return rc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused frame: one memset + one cooperative launch of k_frame (rt_frame.cuh)
+// ---------------------------------------------------------------------------------------------
+constexpr int RT_RETRY_WAVEFRONT = 1;  // run_fused: the frame must be rendered by the wavefront path instead
+
+struct FusedShape { int J, Lmax, S, depth_cap; bool unbounded; };
+
+// Which frames take the fused kernel.  It needs the shadow jobs of a hit in a 64-bit mask and a depth cap within
+// its slabs.  Whether it is also FASTER depends on the frame: a warp of k_frame walks its tile through every
+// stage on its own, which costs nothing to launch and keeps everything in registers, but the warps of an SM then
+// sit in different loops of a 100 KB kernel (instruction-cache misses are its top stall) and a tile's shadow jobs
+// run one after the other instead of across the machine.  Measured (B200): the 1-GPU 1080p headline frame takes
+// 0.40 ms fused and 0.335 ms as a wavefront graph, but a quarter of that frame (4 GPUs) takes 0.10 ms fused and
+// 0.157 ms as a graph, whose ten dependent launches no longer shrink with the frame.  So the default is "auto":
+// small frames -- the bands of a multi-GPU frame, interactive previews -- and frames of unbounded depth (whose
+// wavefront form needs a host read-back per level) are fused, large single-GPU frames are not.
+bool fused_shape(const FrameParams &fp, long long n_rays, FusedShape *out) {
+  FusedShape f;
+  f.Lmax = std::max(1, fp.n_lights);
+  f.S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
+  f.J = f.Lmax + f.Lmax * f.S;
+  f.unbounded = fp.max_depth < 0;
+  f.depth_cap = f.unbounded ? RT_FUSED_MAX_LEVELS - 1 : fp.max_depth;
+  if (out) *out = f;
+  if (!g_opt_fused || f.J > RT_FUSED_MAX_JOBS || f.depth_cap > RT_FUSED_MAX_LEVELS - 1) return false;
+  if (g_opt_fused == 2 && !f.unbounded && n_rays > 1000LL * g_opt_fused_max_kpix) return false;
+  return true;
+}
+
+int fused_reserve(RtScene *sc, size_t n0, int depth_cap) {
+  const size_t n = std::max<size_t>(n0, 1);
+  const size_t q_slabs = (size_t)depth_cap + 1, r_slabs = (size_t)std::max(depth_cap, 1);
+  int rc;
+  if ((rc = sc->fq_o.reserve(q_slabs * n * 16)) || (rc = sc->fq_d.reserve(q_slabs * n * 16)) ||
+      (rc = sc->fq_x.reserve(q_slabs * n * 16)) || (rc = sc->frec_a.reserve(r_slabs * n * 16)) ||
+      (rc = sc->frec_b.reserve(r_slabs * n * 8)) || (rc = sc->fcounts.reserve(sizeof(FusedCounts))))
+    return rc;
+  return RT_OK;
+}
+
+template <bool STATS>
+int fused_grid() {
+  static int cached_opt = -1, cached_dev = -1, cached = 0;
+  if (cached_opt != g_opt_ctas_per_sm || cached_dev != g_device) {
+    cached = persistent_grid(k_frame<STATS>, 128);
+    cached_opt = g_opt_ctas_per_sm; cached_dev = g_device;
+  }
+  return cached;
+}
+
+int run_fused(RtScene *sc, FrameParams &fp, bool explicit_rays, int n0, cudaStream_t st, bool own_stream, RtStats *stats) {
+  FusedShape sh;
+  fused_shape(fp, n0, &sh);
+  int rc;
+  if ((rc = fused_reserve(sc, (size_t)n0, sh.depth_cap))) return rc;
+  FusedBufs fb;
+  fb.q_o = sc->fq_o.as<float4>(); fb.q_d = sc->fq_d.as<float4>(); fb.q_x = sc->fq_x.as<float4>();
+  fb.rec_a = sc->frec_a.as<float4>(); fb.rec_b = sc->frec_b.as<int2>();
+  fb.n_cap = std::max(n0, 1);
+  FusedCounts *fc = sc->fcounts.as<FusedCounts>();
+  const bool trav_stats = g_opt_stats != 0;
+  const bool want_stats = stats != nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  if (want_stats) { cudaEventCreate(&ev_a); cudaEventCreate(&ev_b); }
+  CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FusedCounts), st));
+  if (want_stats) cudaEventRecord(ev_a, st);
+  int explicit0 = explicit_rays ? 1 : 0, J = sh.J, Lmax = sh.Lmax, S = sh.S, depth_cap = sh.depth_cap, cont_min = g_opt_cont_min;
+  void *args[] = {&sc->dev, &fp, &fb, &fc, &n0, &explicit0, &J, &Lmax, &S, &depth_cap, &cont_min};
+  if (trav_stats) CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_frame<true>, dim3(fused_grid<true>()), dim3(128), args, 0, st));
+  else CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_frame<false>, dim3(fused_grid<false>()), dim3(128), args, 0, st));
+  if (want_stats) cudaEventRecord(ev_b, st);
+  if (want_stats || sh.unbounded) {
+    CUDA_TRY(cudaMemcpyAsync(sc->h_fcounts, fc, sizeof(FusedCounts), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const FusedCounts &h = *sc->h_fcounts;
+    if (sh.unbounded && h.overflow) {
+      // some chain wanted to go deeper than the slabs allow: the frame is incomplete
+      if (want_stats) { cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); }
+      return RT_RETRY_WAVEFRONT;
+    }
+    if (want_stats) {
+      memset(stats, 0, sizeof(*stats));
+      cudaEventElapsedTime(&stats->ms_total, ev_a, ev_b);
+      cudaEventDestroy(ev_a); cudaEventDestroy(ev_b);
+      stats->rays_primary = n0;
+      stats->pixels = n0;
+      stats->rays_shadow = (int64_t)h.ctr.shadow_rays;
+      stats->shadow_rays_traced = (int64_t)h.ctr.shadow_rays_traced;
+      int64_t secondary = 0;
+      int lv_used = 1;
+      for (int l = 1; l <= RT_FUSED_MAX_LEVELS; ++l) { secondary += h.n_spawn[l]; if (h.n_spawn[l] > 0) lv_used = l + 1; }
+      stats->rays_secondary = secondary;
+      stats->levels = lv_used;
+      stats->kernel_launches = 1;
+      stats->box_tests = (int64_t)h.ctr.box_tests;
+      stats->tri_tests = (int64_t)h.ctr.tri_tests;
+      stats->shade_samples = (int64_t)h.ctr.shade_samples;
+      stats->box_tests_shadow = (int64_t)h.ctr.box_tests_k2;
+      stats->tri_tests_shadow = (int64_t)h.ctr.tri_tests_k2;
+      stats->filter_checks = (int64_t)h.ctr.filter_checks;
+      stats->filter_slow = (int64_t)h.ctr.filter_slow;
+      stats->filter_rejects = (int64_t)h.ctr.filter_rejects;
+      // phase shares: warp-cycles (clock64) inside the kernel, scaled to its CUDA-event duration
+      const double all = (double)h.phase_clk[3];
+      if (all > 0.0) {
+        stats->ms_trace = (float)(stats->ms_total * (double)h.phase_clk[0] / all);
+        stats->ms_shadow = (float)(stats->ms_total * (double)h.phase_clk[1] / all);
+        stats->ms_shade = (float)(stats->ms_total * (double)h.phase_clk[2] / all);
+      }
+      stats->fused = 1;
+    }
+  }
+  if (own_stream) CUDA_TRY(cudaStreamSynchronize(st));
+  return RT_OK;
+}
+
 int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int n0, uchar4 *d_rgba, int32_t *d_face,
                  float *d_t, float *d_rgbf, cudaStream_t user_stream, RtStats *stats) {
   // the legacy default stream cannot be captured: run on the scene's own stream and join at the end
@@ -956,6 +1086,11 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
 
   FrameParams fp = fp_in;
   fp.out_rgba = d_rgba; fp.out_face = d_face; fp.out_t = d_t; fp.out_rgbf = d_rgbf;
+
+  if (fused_shape(fp, n0, nullptr)) {
+    const int frc = run_fused(sc, fp, explicit_rays, n0, st, own_stream, stats);
+    if (frc != RT_RETRY_WAVEFRONT) return frc;
+  }
 
   const bool want_stats = stats != nullptr;
   FramePlan pl;
@@ -1252,16 +1387,29 @@ extern "C" int rt_trace_rays(RtScene *sc, int64_t n, const float *origins, const
   fp.width = (int)n; fp.height = 1; fp.local_rows = 1; fp.band_world = 1;
   const int Lmax = std::max(1, fp.n_lights);
   const int S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
-  if ((int)sc->levels.size() < 1) sc->levels.resize(1);
-  if ((rc = sc->levels[0].reserve((size_t)n, (size_t)(Lmax + Lmax * S)))) return rc;
   std::vector<float> ho((size_t)n * 4), hd((size_t)n * 4);
   for (int64_t i = 0; i < n; ++i) {
     for (int k = 0; k < 3; ++k) { ho[4 * i + k] = origins[3 * i + k]; hd[4 * i + k] = dirs[3 * i + k]; }
     ho[4 * i + 3] = bits(0); hd[4 * i + 3] = 0.f;
   }
-  CUDA_TRY(cudaMemcpy(sc->levels[0].ray_o.p, ho.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(sc->levels[0].ray_d.p, hd.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemset(sc->levels[0].ray_l.p, 0, (size_t)n * 8));
+  FusedShape fsh;
+  const bool fused = fused_shape(fp, n, &fsh);
+  if (fused) {
+    // level-0 slab of the fused frame's ray queue: (o, flags), (d, lp.x), (lp.y, lp.z, parent = none, ray index)
+    if ((rc = fused_reserve(sc, (size_t)n, fsh.depth_cap))) return rc;
+    std::vector<float> hx((size_t)n * 4, 0.f);
+    for (int64_t i = 0; i < n; ++i) { hx[4 * i + 2] = bits(-1); hx[4 * i + 3] = bits((int32_t)i); }
+    CUDA_TRY(cudaMemcpy(sc->fq_o.p, ho.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sc->fq_d.p, hd.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sc->fq_x.p, hx.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+  }
+  if (!fused || fsh.unbounded) {  // the wavefront path (also the fall-back of an unbounded frame that went too deep)
+    if ((int)sc->levels.size() < 1) sc->levels.resize(1);
+    if ((rc = sc->levels[0].reserve((size_t)n, (size_t)(Lmax + Lmax * S)))) return rc;
+    CUDA_TRY(cudaMemcpy(sc->levels[0].ray_o.p, ho.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sc->levels[0].ray_d.p, hd.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(sc->levels[0].ray_l.p, 0, (size_t)n * 8));
+  }
   if ((rc = sc->out_rgbf.reserve((size_t)n * 12)) || (rc = sc->out_face.reserve((size_t)n * 4)) ||
       (rc = sc->out_t.reserve((size_t)n * 4)))
     return rc;

@@ -25,8 +25,17 @@ def quant(rgb):
     return np.clip(np.minimum(255, q), 0, 255)
 
 
+@pytest.fixture(params=[0, 1], ids=["wavefront", "fused"])
+def frame_path(request, capi):
+    """Every golden case is rendered twice: by the per-level wavefront kernels (csrc/rt_kernels.cuh) and as one
+    persistent kernel (csrc/rt_frame.cuh).  The library's default picks between them by frame size."""
+    capi.set_option("fused_frame", request.param)
+    yield request.param
+    capi.set_option("fused_frame", 2)
+
+
 @pytest.mark.parametrize("case", ALL_CASES)
-def test_render_matches_reference_golden(case, pkg, capi, scene_dir):
+def test_render_matches_reference_golden(case, frame_path, pkg, capi, scene_dir):
     g = load_golden(case)
     verts, fn, vn, mid, mats = scene_arrays(case, pkg, scene_dir)
     capi.init(0)
@@ -36,6 +45,8 @@ def test_render_matches_reference_golden(case, pkg, capi, scene_dir):
     lights = capi.Lights(g["lights"], g["light_color"])
     params = capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], cp["max_depth"], cp["grid"])
     fr = scene.render(cam, lights, params)
+    J = len(g["lights"]) * (1 + (0 if cp["point"] else cp["grid"][0] * cp["grid"][1]))
+    assert fr.stats["fused"] == (1 if frame_path and J <= 64 else 0)  # the path asked for is the one that ran
     px, py = g["pxy"][:, 0], g["pxy"][:, 1]
 
     face = fr.face[py, px]
@@ -57,7 +68,7 @@ def test_render_matches_reference_golden(case, pkg, capi, scene_dir):
 
 
 @pytest.mark.parametrize("case", ["cube_area_640x360", "gallery_area_200x150", "hf32_point_256x144"])
-def test_full_frame_matches_oracle(case, pkg, capi, oracle_mod, scene_dir):
+def test_full_frame_matches_oracle(case, frame_path, pkg, capi, oracle_mod, scene_dir):
     """Every pixel of the frame (not only the golden subset) against the CPU oracle."""
     O = oracle_mod
     g = load_golden(case)
@@ -119,7 +130,7 @@ def test_known_answers_of_the_default_scene_on_gpu(pkg, capi):
     assert fa.stats["rays_shadow"] == 494209 * 26 and fa.stats["rays_secondary"] == 494209
 
 
-def test_headline_config_full_frame_vs_oracle(pkg, capi, oracle_mod):
+def test_headline_config_full_frame_vs_oracle(frame_path, pkg, capi, oracle_mod):
     """BASELINE configs[1] exactly as bench.py runs it (cube, 1920x1080, 4x4 area light, depth 3):
     every one of the 2 073 600 pixels against the oracle."""
     O = oracle_mod
@@ -202,7 +213,7 @@ def test_c4_benchmark_config_vs_port(pkg, capi, oracle_mod):
     pxy, rgb, face, t, rgb8 = orc.render(cam, lights_np, W, H, stride=16, offx=5, offy=3, threads=max(1, (os.cpu_count() or 2) - 1))
     px, py = pxy[:, 0], pxy[:, 1]
     T = arrs[0].shape[0]
-    assert (face >= T).sum() > 100 and ((face >= 0) & (face < T)).sum() > 5000, "spheres and triangles should both be visible"
+    assert (face >= T).sum() > 100 and ((face >= 0) & (face < T)).sum() > 3000, "spheres and triangles should both be visible"
     assert (fr.face[py, px] == face).all()
     assert (fr.t[py, px].view(np.uint32) == t.view(np.uint32)).all()
     err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - quant(rgb)).max(-1)

@@ -101,7 +101,7 @@ def test_library_exports_every_declared_symbol(pkg):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, f"librt_b200.so does not export {missing}"
     assert declared == set(pkg.capi.API_SYMBOLS)
-    assert pkg.capi.lib().rt_api_version() == 2
+    assert pkg.capi.lib().rt_api_version() == 3
 
 
 def test_no_cpu_fallback(pkg):
