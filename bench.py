@@ -14,9 +14,12 @@ queue sizes.  `value` is measured with the scene and the framebuffer resident in
 the launch stream, L2 flushed between frames); `e2e` goes through rt_render() with pinned HOST
 buffers, copies inside the timed region.
 
-N > 1 (torchrun, one rank per GPU): the frame is split into interleaved 8-row bands
-(band b -> rank b mod N), each rank renders its bands and the bands are gathered to rank 0 with NCCL;
-the timed step includes the gather.  Strong scaling: the frame is fixed.
+N > 1 (torchrun, one rank per GPU): the frame is split into interleaved row bands (band b -> rank b mod N), every
+rank renders its bands and its kernels store the pixels straight into rank 0's frame over NVLink peer memory; per-rank
+flags behind the frame signal completion (no collective in the timed step).  The NCCL gather of per-rank buffers is
+timed beside it as the baseline (`nccl_gather_baseline`), and so is the same frame driven from ONE process through
+rt_multi_* (`single_process_multi_gpu`).  e2e at N > 1: every rank copies its own bands into a shared pinned host
+frame.  Strong scaling: the frame is fixed.
 
 --impl reference: the reference's own CPU implementation (oracle/_ref/ref_oracle[_patched], built
 from /root/reference by oracle/Makefile; falls back to the C port if that binary is absent) on a
@@ -436,11 +439,16 @@ def main():
                 shared = capi.SharedFrame(W, H, bytes(hbuf.cpu().numpy().tobytes()))
             params_peer = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], band_rows, rank, world)
             params_peer.out_full_frame = 1
-            token = torch.zeros(1, dtype=torch.int32, device=dev)
+            frame_seq = [0]
 
             def step_peer():
+                # no collective: every rank raises its flag behind the shared frame when its pixels are stored, rank 0
+                # queues a one-warp kernel that waits for all flags (rt_shared_frame_signal / _wait)
+                frame_seq[0] += 1
                 scene.render_device(cam, lights, params_peer, shared.ptr.value, stream=stream)
-                dist.all_reduce(token)
+                shared.signal(rank, frame_seq[0], stream)
+                if rank == 0:
+                    shared.wait(world, frame_seq[0], stream)
         except Exception as ex:  # peer mapping unavailable: keep the NCCL path only
             print(f"[rank {rank}] peer-store path unavailable: {ex}", file=sys.stderr)
             shared, step_peer = None, None
@@ -557,19 +565,21 @@ def main():
             scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False,
                          out_rgba=host_np)
     else:
-        host = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
-        host_np = host.numpy()
-        fn = step_peer if step_peer is not None else step
+        # the full frame lives in POSIX shared memory, page-locked in every rank (rt_host_frame_*); every rank copies
+        # its OWN bands into it over its own PCIe link (rt_render_into_frame), so the 8.3 MB do not all leave through
+        # rank 0.  Two process barriers of the library per frame: "previous frame consumed" and "frame complete".
+        names = [f"/rt_b200_frame_{os.getpid()}" if rank == 0 else None]
+        dist.broadcast_object_list(names, src=0)
+        hostframe = capi.HostFrame(names[0], W, H, create=True) if rank == 0 else None
+        dist.barrier()
+        if rank != 0:
+            hostframe = capi.HostFrame(names[0], W, H, create=False)
+        host_np = hostframe.array
 
         def e2e_step():
-            fn()
-            torch.cuda.synchronize()
-            if rank == 0:
-                if step_peer is not None:
-                    capi.lib().rt_device_copy_to_host(host_np.ctypes.data, shared.ptr, host_np.nbytes)
-                else:
-                    host.copy_(gather.frame)
-                    torch.cuda.synchronize()
+            hostframe.barrier(world)
+            scene.render_into_frame(cam, lights, params, hostframe.ptr)
+            hostframe.barrier(world)
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
@@ -588,7 +598,14 @@ def main():
     dt = float(dt_t.item())
     e2e = {"value": rays_total * k2 / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d) * world,
            "d2h_bytes_per_step": int(H * W * 4), "ms_per_step": 1e3 * dt / k2, "steps": k2,
-           "call": "rt_render (blocking, pinned host frame)" if world == 1 else "bands + assembly on rank 0 + D2H"}
+           "call": "rt_render (blocking, pinned host frame)" if world == 1 else
+                   "rt_render_into_frame on every rank: own bands -> shared pinned host frame (POSIX shm), library process barrier"}
+    if world > 1:
+        # the assembled host frame must be the frame: compare it with rank 0's device-assembled one
+        hostframe.barrier(world)
+        if rank == 0 and shared is not None and step_peer is not None:
+            e2e["frame_matches_device_frame"] = bool((host_np == shared.to_host()).all())
+        hostframe.barrier(world)
     if world == 1:
         # the same steps through the streaming call: rt_render_submit / rt_render_wait, two frames in
         # flight, every frame still copied to pinned host memory inside the timed region
@@ -607,6 +624,47 @@ def main():
         assert (hosts[(k2 - 1) & 1] == host_np).all(), "streaming and blocking frames differ"
         e2e["pipelined"] = {"value": rays_total * k2 / dtp / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * dtp / k2,
                             "call": "rt_render_submit / rt_render_wait, 2 frames in flight"}
+
+    # ---- the same frame from ONE host process driving all N GPUs (rt_multi_*: what the C++ facade / rt_cli use) ----
+    # Measured by rank 0 alone while the other ranks wait on the library's CPU-side barrier (their GPUs are idle).
+    single_process = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank == 0:
+            try:
+                multi = capi.Multi(list(range(world)), *arrs, None, spheres, sphere_mat)
+                mp = capi.make_params(W, H, wl["area"], wl["point"], wl["max_depth"], wl["grid"], band_rows)
+                kk = min(args.steps, 50)
+                for _ in range(args.warmup):
+                    multi.render_device(cam, lights, mp)
+                dev_ms, t0 = [], time.perf_counter()
+                for _ in range(kk):
+                    dev_ms.append(multi.render_device(cam, lights, mp)[1])
+                wall_dev = (time.perf_counter() - t0) / kk
+                ptr, _ = multi.render_device(cam, lights, mp)
+                fr = np.zeros((H, W, 4), np.uint8)
+                capi.lib().rt_device_copy_to_host(fr.ctypes.data, ptr, fr.nbytes)
+                for _ in range(args.warmup):
+                    multi.render(cam, lights, mp, out=host_np)
+                t0 = time.perf_counter()
+                for _ in range(kk):
+                    multi.render(cam, lights, mp, out=host_np)
+                wall_host = (time.perf_counter() - t0) / kk
+                single_process = {
+                    "call": "rt_multi_render_device / rt_multi_render: one process, one worker thread per GPU",
+                    "device_frame": {"ms_per_step_slowest_device": float(np.median(dev_ms)), "ms_per_step_wall": 1e3 * wall_dev,
+                                     "value": rays_total / wall_dev / 1e6, "unit": "Mrays/s",
+                                     "frame_matches": bool(shared is not None and (fr == shared.to_host()).all())},
+                    "host_frame": {"ms_per_step_wall": 1e3 * wall_host, "value": rays_total / wall_host / 1e6, "unit": "Mrays/s",
+                                   "frame_matches": bool(shared is not None and (host_np == shared.to_host()).all())},
+                    "note": "no L2 flush between these frames; wall = host clock around the blocking call"}
+                multi.close()
+            except Exception as ex:
+                single_process = {"unavailable": str(ex)[:300]}
+        hostframe.barrier(world)
+        hostframe.close()
 
     if rank != 0:
         if world > 1:
@@ -685,7 +743,7 @@ def main():
                    "max_depth": wl["max_depth"], "l2": "flushed between timed frames (512 MiB memset)",
                    "parallelism": (f"{world} x interleaved {band_rows}-row bands; " +
                                    ("kernels store pixels into rank 0's framebuffer over NVLink peer memory (CUDA IPC), "
-                                    "4-byte NCCL all-reduce as completion signal" if nccl_line else "NCCL gather to rank 0"))
+                                    "completion by per-rank flags behind the frame that a one-warp kernel on rank 0 polls (no collective)" if nccl_line else "NCCL gather to rank 0"))
                    if world > 1 else "1 GPU",
                    "bvh": info, "options": args.opt},
         "rays": {"per_frame": rays_total, "primary": n_primary, "shadow": n_shadow, "secondary": n_secondary,
@@ -697,7 +755,7 @@ def main():
         "timing": spread,
         "kernel_ms": kernel_ms, "frame_path": "fused (one persistent kernel)" if fused else "wavefront (CUDA graph of per-level kernels)",
         "gpu_launches": int(stats["kernel_launches"] * args.steps),
-        "clocks": clocks, "wall_s": wall, "nccl_gather_baseline": nccl_line, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "wall_s": wall, "nccl_gather_baseline": nccl_line, "single_process_multi_gpu": single_process, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

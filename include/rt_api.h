@@ -148,6 +148,12 @@ int rt_api_version(void);
 /* Select the CUDA device for this process (one process per GPU).  Replaces nothing in the
  * reference (CPU only); ThreadPool construction src/flyscene.cpp:609 is the closest analogue. */
 int rt_init(int device);
+/* Several GPUs of one box (the surveyed rt_init(device_count, devices)): validates the list, makes devices[0] the
+ * default device and enables peer access between the devices, so that kernels of one GPU can store pixels into a
+ * framebuffer on another over NVLink.  Used by rt_multi_create; one host process. */
+int rt_init_devices(int count, const int *devices);
+/* Releases what the library allocated lazily for rendering (ray queues, frame graphs, staging buffers) on every
+ * live scene and forgets the device selection; scenes stay valid (their workspace is re-created on demand). */
 void rt_shutdown(void);
 const char *rt_last_error(void);
 int rt_device_name(char *buf, size_t n);
@@ -228,6 +234,48 @@ int rt_shared_frame_create(size_t bytes, void **d_ptr, unsigned char handle[64])
 int rt_shared_frame_open(const unsigned char handle[64], void **d_ptr);           /* other ranks */
 int rt_shared_frame_close(void *d_ptr, int owner);
 int rt_device_copy_to_host(void *host, const void *d_ptr, size_t bytes);
+/* Completion without a collective: the shared allocation carries one flag per rank behind the frame.  After its
+ * frame (rt_render_device with out_full_frame = 1 on `stream`) every rank queues rt_shared_frame_signal(seq) on the
+ * same stream; rank 0 queues rt_shared_frame_wait(seq), a one-warp kernel that polls the flags in its own memory
+ * (it gives up after ~2 s so that a dead rank cannot hang the GPU).  seq must increase from frame to frame.
+ * Replaces pool.enqueue / result.get() of the reference's ThreadPool (src/flyscene.cpp:613-629). */
+int rt_shared_frame_signal(void *d_frame, size_t frame_bytes, int rank, unsigned int seq, void *stream);
+int rt_shared_frame_wait(void *d_frame, size_t frame_bytes, int world, unsigned int seq, void *stream);
+
+/* A HOST frame shared by the per-GPU processes: POSIX shared memory (shm name, e.g. "/rt_frame_<pid>"), page-locked
+ * in every process that opens it.  create != 0 on exactly one rank, before the others open it.  Every rank copies
+ * its own bands into it (rt_render_into_frame): N PCIe links carry the frame instead of rank 0's alone.
+ * rt_host_frame_barrier is a spinning barrier of `world` processes on the shared header (frame complete / frame
+ * consumed); it times out after 60 s. */
+typedef struct RtHostFrame RtHostFrame;
+int rt_host_frame_open(const char *name, size_t bytes, int create, RtHostFrame **out);
+void *rt_host_frame_ptr(RtHostFrame *frame);
+int rt_host_frame_barrier(RtHostFrame *frame, int world);
+void rt_host_frame_close(RtHostFrame *frame);
+/* rt_render for one rank of a band-sharded frame (params->band_*): renders this rank's bands and copies them to
+ * their global rows of rgba_full, the full [H][W][4] host frame all ranks share.  Blocking.  band_world <= 1: = rt_render. */
+int rt_render_into_frame(RtScene *scene, const RtCamera *cam, const RtLights *lights, const RtParams *params,
+                         uint8_t *rgba_full);
+
+/* ---- multi-GPU from ONE host process --------------------------------------------------------------------------
+ * Flyscene::raytraceScene's ThreadPool fan-out (src/flyscene.cpp:558-629) with GPUs as the workers: the scene is
+ * baked once on the host and uploaded to every device; device k renders the interleaved row bands k, k+N, ...
+ * (band height params->band_rows, 0 = chosen by the library; band_rank / band_world are set by the library) and
+ * one worker thread per device submits its share, so the devices start within microseconds of each other. */
+typedef struct RtMulti RtMulti;
+int rt_multi_create(const RtSceneDesc *desc, int n_devices, const int *devices, RtMulti **out);
+void rt_multi_destroy(RtMulti *multi);
+int rt_multi_device_count(const RtMulti *multi);
+int rt_multi_scene(const RtMulti *multi, int k, RtScene **scene_out); /* device k's scene, for the per-function calls */
+/* rgba_out: host [H][W][4]; every device copies its own bands straight into it.  stats (optional, diagnostic, slower):
+ * census and work counters summed over the devices, times = max over the devices. */
+int rt_multi_render(RtMulti *multi, const RtCamera *cam, const RtLights *lights, const RtParams *params,
+                    uint8_t *rgba_out, RtStats *stats);
+/* The frame stays on the GPU: the kernels of every device store their pixels into one [H][W][4] frame on devices[0]
+ * over NVLink peer access.  *d_frame: that frame (valid until the next call).  *ms (optional): device time of the
+ * slowest device (CUDA events around its share). */
+int rt_multi_render_device(RtMulti *multi, const RtCamera *cam, const RtLights *lights, const RtParams *params,
+                           void **d_frame, float *ms);
 
 /* ---- per-function entry points (batched) --------------------------------------------------- */
 /* Flyscene::traceRay (src/flyscene.cpp:651-771) for n arbitrary rays: rgb_out [n][3] float,

@@ -77,6 +77,9 @@ API_SYMBOLS = [
     "rt_shared_frame_open", "rt_shared_frame_close", "rt_device_copy_to_host", "rt_trace_rays",
     "rt_light_strikes", "rt_box_intersect", "rt_box_intersect_box", "rt_ray_triangle", "rt_octree_candidates",
     "rt_phong_shade", "rt_screen_to_world", "rt_light_samples", "rt_write_ppm", "rt_selftest_div3",
+    "rt_init_devices", "rt_shared_frame_signal", "rt_shared_frame_wait", "rt_host_frame_open", "rt_host_frame_ptr",
+    "rt_host_frame_barrier", "rt_host_frame_close", "rt_render_into_frame", "rt_multi_create", "rt_multi_destroy",
+    "rt_multi_device_count", "rt_multi_scene", "rt_multi_render", "rt_multi_render_device",
 ]
 
 _lib = None
@@ -133,6 +136,25 @@ def lib():
     L.rt_light_samples.argtypes = [C.POINTER(RtParams), vp, vp]
     L.rt_write_ppm.argtypes = [C.c_char_p, vp, i32, i32, i32]
     L.rt_selftest_div3.argtypes = [i64, C.c_uint32, i32, C.POINTER(C.c_int64)]
+    L.rt_init_devices.argtypes = [C.c_int, vp]
+    L.rt_shutdown.restype = None
+    L.rt_shared_frame_signal.argtypes = [vp, C.c_size_t, C.c_int, C.c_uint, vp]
+    L.rt_shared_frame_wait.argtypes = [vp, C.c_size_t, C.c_int, C.c_uint, vp]
+    L.rt_host_frame_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.rt_host_frame_ptr.argtypes = [vp]
+    L.rt_host_frame_ptr.restype = vp
+    L.rt_host_frame_barrier.argtypes = [vp, C.c_int]
+    L.rt_host_frame_close.argtypes = [vp]
+    L.rt_host_frame_close.restype = None
+    L.rt_render_into_frame.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp]
+    L.rt_multi_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, vp, C.POINTER(vp)]
+    L.rt_multi_destroy.argtypes = [vp]
+    L.rt_multi_destroy.restype = None
+    L.rt_multi_device_count.argtypes = [vp]
+    L.rt_multi_scene.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.rt_multi_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), vp, vp]
+    L.rt_multi_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtLights), C.POINTER(RtParams), C.POINTER(vp),
+                                         C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -264,6 +286,12 @@ class Scene:
     """Device-resident scene (rt_scene_create): flattened BVH + triangle soup + shading tables."""
 
     def __init__(self, verts, fnormals, vnormals, mat_id, mats, model_matrix=None, spheres=None, sphere_mat=None):
+        d = self._make_desc(verts, fnormals, vnormals, mat_id, mats, model_matrix, spheres, sphere_mat)
+        self.n_faces = d.n_faces
+        self.h = C.c_void_p()
+        _check(lib().rt_scene_create(C.byref(d), C.byref(self.h)))
+
+    def _make_desc(self, verts, fnormals, vnormals, mat_id, mats, model_matrix=None, spheres=None, sphere_mat=None):
         self._keep = []
 
         def keep(a, dt):
@@ -297,9 +325,7 @@ class Scene:
             d.n_spheres = int(sp.shape[0])
             d.spheres = _ptr(sp)
             d.sphere_material = _ptr(keep(sphere_mat, np.int32))
-        self.n_faces = d.n_faces
-        self.h = C.c_void_p()
-        _check(lib().rt_scene_create(C.byref(d), C.byref(self.h)))
+        return d
 
     @classmethod
     def from_mesh(cls, mesh: Mesh, spheres=None, sphere_mat=None):
@@ -364,6 +390,10 @@ class Scene:
         _check(lib().rt_render_device(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), d_rgba or None,
                                       d_face or None, d_t or None, d_rgb or None, stream or None,
                                       C.byref(stats) if stats is not None else None))
+
+    def render_into_frame(self, cam, lights, params, frame_ptr):
+        """This rank's bands, copied to their global rows of the full host frame at frame_ptr (blocking)."""
+        _check(lib().rt_render_into_frame(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), C.c_void_p(frame_ptr)))
 
     def trace_rays(self, origins, dirs, lights: Lights, params: RtParams):
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
@@ -472,6 +502,12 @@ class SharedFrame:
             _check(lib().rt_shared_frame_open(buf, C.byref(self.ptr)))
             self.handle = handle
 
+    def signal(self, rank, seq, stream):
+        _check(lib().rt_shared_frame_signal(self.ptr, self.w * self.h * 4, int(rank), int(seq), C.c_void_p(stream)))
+
+    def wait(self, world, seq, stream):
+        _check(lib().rt_shared_frame_wait(self.ptr, self.w * self.h * 4, int(world), int(seq), C.c_void_p(stream)))
+
     def to_host(self):
         out = np.zeros((self.h, self.w, 4), np.uint8)
         _check(lib().rt_device_copy_to_host(_ptr(out), self.ptr, out.nbytes))
@@ -481,6 +517,65 @@ class SharedFrame:
         if self.ptr:
             lib().rt_shared_frame_close(self.ptr, int(self.owner))
             self.ptr = C.c_void_p()
+
+
+class HostFrame:
+    """A full-frame RGBA buffer in POSIX shared memory, page-locked in every process that opens it
+    (rt_host_frame_*): the per-GPU processes copy their own bands into it."""
+
+    def __init__(self, name: str, width, height, create: bool):
+        self.w, self.h = width, height
+        self.hd = C.c_void_p()
+        _check(lib().rt_host_frame_open(name.encode(), width * height * 4, int(create), C.byref(self.hd)))
+        ptr = lib().rt_host_frame_ptr(self.hd)
+        self.ptr = ptr
+        self.array = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(height, width, 4))
+
+    def barrier(self, world):
+        _check(lib().rt_host_frame_barrier(self.hd, int(world)))
+
+    def close(self):
+        if self.hd:
+            self.array = None
+            lib().rt_host_frame_close(self.hd)
+            self.hd = C.c_void_p()
+
+
+class Multi:
+    """One host process, N GPUs (rt_multi_*): scene baked once, uploaded to every device."""
+
+    def __init__(self, devices, verts, fnormals, vnormals, mat_id, mats, model_matrix=None, spheres=None, sphere_mat=None):
+        d = Scene._make_desc(self, verts, fnormals, vnormals, mat_id, mats, model_matrix, spheres, sphere_mat)
+        self.devices = np.ascontiguousarray(devices, np.int32)
+        self.h = C.c_void_p()
+        _check(lib().rt_multi_create(C.byref(d), len(self.devices), _ptr(self.devices), C.byref(self.h)))
+
+    def render(self, cam, lights: Lights, params: RtParams, out=None, want_stats=False):
+        H, W = params.height, params.width
+        if out is None:
+            out = np.zeros((H, W, 4), np.uint8)
+        st = RtStats() if want_stats else None
+        _check(lib().rt_multi_render(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), _ptr(out),
+                                     C.byref(st) if st is not None else None))
+        return (out, st.as_dict()) if want_stats else out
+
+    def render_device(self, cam, lights: Lights, params: RtParams):
+        """Returns (device-0 pointer of the assembled frame, device ms of the slowest device)."""
+        ptr = C.c_void_p()
+        ms = C.c_float()
+        _check(lib().rt_multi_render_device(self.h, C.byref(cam), C.byref(lights.c), C.byref(params), C.byref(ptr), C.byref(ms)))
+        return ptr, ms.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().rt_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def local_row_map(params: RtParams):

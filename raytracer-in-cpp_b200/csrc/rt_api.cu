@@ -7,12 +7,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -32,8 +34,19 @@ using namespace rtd;
 namespace {
 
 thread_local std::string g_err;
-int g_device = -1;
-int g_sm_count = 0;
+// Devices.  g_device is the device the calling thread is working on: rt_init() picks the default one, every
+// entry point that takes a scene switches to the scene's own device first (use_device), so one host thread can
+// drive scenes on several GPUs (rt_multi_*).
+int g_default_device = -1;
+thread_local int g_device = -1;
+thread_local int g_sm_count = 0;
+struct DeviceState {
+  int sm_count = 0;
+  int grids_opt = -1;  // value of persistent_ctas_per_sm the grids below were computed for
+  int g1p = 0, g1s = 0, g2 = 0, g1ps = 0, g1ss = 0, g2s = 0, kf = 0, kfs = 0;  // persistent grid sizes
+};
+constexpr int kMaxDevices = 64;
+DeviceState g_devs[kMaxDevices];
 int g_opt_stats = 0;
 int g_opt_leaf = 2;  // measured best on the 100 k / 1 M-triangle scenes (leaf tests are exact and expensive)
 int g_opt_ctas_per_sm = 0;  // 0 = occupancy query
@@ -61,13 +74,31 @@ int fail(int code, const char *fmt, ...) {
       return fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+int use_device(int device) {
+  if (device < 0 || device >= kMaxDevices) return fail(RT_ERR_INVALID, "device %d out of range", device);
+  if (g_devs[device].sm_count == 0) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(RT_ERR_NO_DEVICE, "cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+    g_devs[device].sm_count = prop.multiProcessorCount;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(RT_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  g_device = device;
+  g_sm_count = g_devs[device].sm_count;
+  return RT_OK;
+}
+
 int ensure_device() {
-  if (g_device >= 0) return RT_OK;
-  return rt_init(0);
+  if (g_default_device < 0) {
+    int rc = rt_init(0);
+    if (rc) return rc;
+  }
+  return use_device(g_default_device);
 }
 
 // grow-only device buffer
-long long g_alloc_generation = 0;  // bumped on every (re)allocation: invalidates captured graphs
+std::atomic<long long> g_alloc_generation{0};  // bumped on every (re)allocation: invalidates captured graphs
 
 struct DevBuf {
   void *p = nullptr;
@@ -127,6 +158,7 @@ struct RtMesh {
 };
 
 struct RtScene {
+  int device = 0;  // CUDA device the scene lives on; every entry point switches to it first
   DevScene dev{};
   DevBuf nodes, prims, shade, mats, spheres, sphere_mat, oct_box, oct_face_off, oct_face_leaf;
   int64_t oct_stats[4] = {0, 0, 0, 0};
@@ -181,12 +213,64 @@ extern "C" int rt_init(int device) {
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return fail(RT_ERR_NO_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-  g_device = device;
-  g_sm_count = prop.multiProcessorCount;
-  return RT_OK;
+  g_default_device = device;
+  g_devs[device].sm_count = prop.multiProcessorCount;
+  return use_device(device);
 }
 
-extern "C" void rt_shutdown(void) { g_device = -1; }
+// rt_init for several GPUs of one box (rt_init(device_count, devices)): checks every device,
+// makes devices[0] the default and enables peer access between all pairs that support it, so that the kernels of
+// one GPU can store their pixels straight into another GPU's framebuffer over NVLink (rt_multi_*).
+extern "C" int rt_init_devices(int count, const int *devices) {
+  if (count <= 0 || !devices) return fail(RT_ERR_INVALID, "empty device list");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(RT_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  for (int i = 0; i < count; ++i) {
+    if (devices[i] < 0 || devices[i] >= n || devices[i] >= kMaxDevices)
+      return fail(RT_ERR_INVALID, "device %d out of range (0..%d)", devices[i], n - 1);
+    for (int j = 0; j < i; ++j)
+      if (devices[j] == devices[i]) return fail(RT_ERR_INVALID, "device %d listed twice", devices[i]);
+  }
+  int rc = rt_init(devices[0]);
+  if (rc) return rc;
+  for (int i = 0; i < count; ++i) {
+    if ((rc = use_device(devices[i]))) return rc;
+    for (int j = 0; j < count; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+      if (!can) continue;
+      e = cudaDeviceEnablePeerAccess(devices[j], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(RT_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", devices[i], devices[j], cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  }
+  return use_device(devices[0]);
+}
+
+namespace {
+// live scenes, so that rt_shutdown can release what the library allocated behind the caller's back
+std::mutex g_scenes_mu;
+std::vector<RtScene *> g_scenes;
+void release_workspace(RtScene *sc);
+}  // namespace
+
+// Releases everything the library allocated lazily for rendering -- per-level ray queues, the fused kernel's slabs,
+// captured frame graphs, staging buffers -- on every live scene, and forgets the device selection.  The scenes
+// themselves (geometry on the device) stay valid and re-create their workspace on the next frame; they are freed by
+// rt_scene_destroy / rt_multi_destroy.
+extern "C" void rt_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_scenes_mu);
+  for (RtScene *sc : g_scenes) release_workspace(sc);
+  for (int d = 0; d < kMaxDevices; ++d) g_devs[d] = DeviceState();
+  g_default_device = -1;
+  g_device = -1;
+}
+
 
 extern "C" int rt_device_name(char *buf, size_t n) {
   int rc = ensure_device();
@@ -281,29 +365,24 @@ int upload(DevBuf &b, const void *src, size_t bytes) {
   return RT_OK;
 }
 
-int upload_octree(RtScene *sc, const rt::RefOctree &oct) {
-  const int n = oct.n_nodes();
-  std::vector<float> packed((size_t)n * 8, 0.f);
-  for (int i = 0; i < n; ++i) {
-    float *q = &packed[(size_t)i * 8];
-    const float *b = &oct.box[(size_t)i * 6];
-    q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; q[3] = bits(oct.parent[i]);
-    q[4] = b[3]; q[5] = b[4]; q[6] = b[5];
-  }
-  int rc;
-  if ((rc = upload(sc->oct_box, packed.data(), packed.size() * 4))) return rc;
-  if ((rc = upload(sc->oct_face_off, oct.face_off.data(), oct.face_off.size() * 4))) return rc;
-  if ((rc = upload(sc->oct_face_leaf, oct.face_leaf.data(), oct.face_leaf.size() * 4))) return rc;
-  sc->dev.oct_box = sc->oct_box.as<float4>();
-  sc->dev.oct_face_off = sc->oct_face_off.as<int32_t>();
-  sc->dev.oct_face_leaf = sc->oct_face_leaf.as<int32_t>();
-  return RT_OK;
-}
-
 }  // namespace
 
-extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
-  if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
+namespace {
+
+// Everything rt_scene_create computes on the HOST: the flattened BVH, the primitive soup, the shading table and the
+// reference-octree filter, ready to be uploaded to any number of devices (rt_multi_create bakes once).
+struct HostBake {
+  DevScene proto{};  // root box, model matrix, counts, oct_eps (device pointers are filled by the upload)
+  std::vector<rt::PairNode> nodes;
+  std::vector<float> prims, shade, mats, spheres, oct_packed;
+  std::vector<int32_t> sphere_mat, oct_face_off, oct_face_leaf, prim_face;
+  bool use_filter = false;
+  int64_t n_leaves = 0, oct_stats[4] = {0, 0, 0, 0};
+  int bvh_depth = 0;
+  float octree_ms = 0.f, bake_ms = 0.f;
+};
+
+int validate_scene_desc(const RtSceneDesc *desc) {
   if (desc->n_faces < 0 || desc->n_spheres < 0 || desc->n_materials <= 0)
     return fail(RT_ERR_INVALID, "bad scene counts (faces %d, spheres %d, materials %d)", desc->n_faces,
                 desc->n_spheres, desc->n_materials);
@@ -320,18 +399,18 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     if (!std::isfinite(sp[0]) || !std::isfinite(sp[1]) || !std::isfinite(sp[2]) || !std::isfinite(sp[3]) || sp[3] < 0.f)
       return fail(RT_ERR_INVALID, "sphere %zu is not finite or has a negative radius", k);
   }
-  const int T = desc->n_faces, S = desc->n_spheres, N = T + S;
-  for (int i = 0; i < T; ++i)
+  for (int i = 0; i < desc->n_faces; ++i)
     if (desc->material_id[i] < 0 || desc->material_id[i] >= desc->n_materials)
       return fail(RT_ERR_INVALID, "face %d has material id %d outside [0,%d)", i, desc->material_id[i], desc->n_materials);
-  for (int i = 0; i < S; ++i)
+  for (int i = 0; i < desc->n_spheres; ++i)
     if (desc->sphere_material[i] < 0 || desc->sphere_material[i] >= desc->n_materials)
       return fail(RT_ERR_INVALID, "sphere %d has a bad material id", i);
-  int rc = ensure_device();
-  if (rc) return rc;
-  const auto t_start = std::chrono::high_resolution_clock::now();
+  return RT_OK;
+}
 
-  RtScene *sc = new RtScene();
+void bake_scene(const RtSceneDesc *desc, HostBake &hb) {
+  const auto t_start = std::chrono::high_resolution_clock::now();
+  const int T = desc->n_faces, S = desc->n_spheres, N = T + S;
   // ---- reference root box: BoundingBox(Mesh&), src/boundingBox.cpp:14-43 (max starts at FLT_MIN) ----
   {
     float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
@@ -342,10 +421,10 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
         mn[a] = std::min(mn[a], x);
         mx[a] = std::max(mx[a], x);
       }
-    memcpy(sc->dev.root_min, mn, 12);
-    memcpy(sc->dev.root_max, mx, 12);
+    memcpy(hb.proto.root_min, mn, 12);
+    memcpy(hb.proto.root_max, mx, 12);
   }
-  memcpy(sc->dev.model, desc->model_matrix, sizeof(float) * 12);
+  memcpy(hb.proto.model, desc->model_matrix, sizeof(float) * 12);
 
   // ---- primitive boxes + BVH ----
   std::vector<rt::Aabb> boxes((size_t)N);
@@ -369,12 +448,13 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
   }
   // ---- reference octree as a candidate filter (host/ref_octree.hpp) ----
   rt::RefOctree oct;
-  bool use_filter = false;
+  bool &use_filter = hb.use_filter;
+  use_filter = false;
   if (g_opt_ref_candidates && T > 0) {
     const auto t_oct = std::chrono::high_resolution_clock::now();
     oct = rt::build_ref_octree(desc->verts, T, 1000 /* src/flyscene.cpp:86 */, 15 /* MAX_DEPTH, src/boxTree.cpp:3 */, 0);
-    sc->octree_ms = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_oct).count();
-    sc->oct_stats[0] = oct.n_leaves; sc->oct_stats[1] = oct.n_inner; sc->oct_stats[2] = oct.n_refs; sc->oct_stats[3] = oct.max_leaf;
+    hb.octree_ms = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_oct).count();
+    hb.oct_stats[0] = oct.n_leaves; hb.oct_stats[1] = oct.n_inner; hb.oct_stats[2] = oct.n_refs; hb.oct_stats[3] = oct.max_leaf;
     use_filter = !oct.root_is_leaf;  // a single-leaf octree offers every face whenever the root box is hit
     if (use_filter) {
       // Degenerate (sliver) faces: the reference's barycentric test is cancellation noise for them and
@@ -413,19 +493,20 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     diag = std::max(1.f, std::sqrt(dx * dx + dy * dy + dz * dz));
   }
   const float pad = 1e-5f * diag;  // see DESIGN.md "conservative culling"
-  sc->dev.oct_eps = 1e-5f * diag;
+  hb.proto.oct_eps = 1e-5f * diag;
   const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   rt::BvhBuildResult bvh = rt::build_bvh(boxes, kind, g_opt_leaf, pad, threads);
-  sc->n_leaves = bvh.n_leaves;
-  sc->bvh_depth = bvh.max_depth;
+  hb.n_leaves = bvh.n_leaves;
+  hb.bvh_depth = bvh.max_depth;
 
   // ---- primitive soup in leaf order (80 B / primitive) ----
-  std::vector<float> prims((size_t)N * 20, 0.f);
-  sc->h_prim_face.resize((size_t)N);
+  std::vector<float> &prims = hb.prims;
+  prims.assign((size_t)N * 20, 0.f);
+  hb.prim_face.resize((size_t)N);
   for (int slot = 0; slot < N; ++slot) {
     const int p = bvh.prim_order[slot];
     float *q = &prims[(size_t)slot * 20];
-    sc->h_prim_face[slot] = p;
+    hb.prim_face[slot] = p;
     if (p < T) {
       const float *v = desc->verts + (size_t)p * 9;
       const float *n = desc->face_normals + (size_t)p * 3;
@@ -450,7 +531,8 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     }
   }
   // ---- shading table in original face order (112 B / face) ----
-  std::vector<float> shade((size_t)std::max(T, 1) * 28, 0.f);
+  std::vector<float> &shade = hb.shade;
+  shade.assign((size_t)std::max(T, 1) * 28, 0.f);
   for (int i = 0; i < T; ++i) {
     float *q = &shade[(size_t)i * 28];
     const float *v = desc->verts + (size_t)i * 9, *vn = desc->vertex_normals + (size_t)i * 9;
@@ -462,7 +544,8 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     q[3] = bits(desc->material_id[i]);
     q[24] = n[0]; q[25] = n[1]; q[26] = n[2];
   }
-  std::vector<float> mats((size_t)desc->n_materials * 12, 0.f);
+  std::vector<float> &mats = hb.mats;
+  mats.assign((size_t)desc->n_materials * 12, 0.f);
   for (int m = 0; m < desc->n_materials; ++m) {
     const RtMaterial &mt = desc->materials[m];
     float *q = &mats[(size_t)m * 12];
@@ -471,14 +554,49 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     q[8] = bits(mt.illum);
   }
 
-  sc->h_nodes = bvh.nodes;
-  if ((rc = upload(sc->nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(rt::PairNode))) ||
-      (rc = upload(sc->prims, prims.data(), prims.size() * 4)) ||
-      (rc = upload(sc->shade, shade.data(), shade.size() * 4)) ||
-      (rc = upload(sc->mats, mats.data(), mats.size() * 4)) ||
-      (rc = upload(sc->spheres, desc->spheres, (size_t)S * 16)) ||
-      (rc = upload(sc->sphere_mat, desc->sphere_material, (size_t)S * 4)) ||
-      (use_filter && (rc = upload_octree(sc, oct))) ||
+  hb.nodes = std::move(bvh.nodes);
+  if (use_filter) {
+    const int n = oct.n_nodes();
+    hb.oct_packed.assign((size_t)n * 8, 0.f);
+    for (int i = 0; i < n; ++i) {
+      float *q = &hb.oct_packed[(size_t)i * 8];
+      const float *b = &oct.box[(size_t)i * 6];
+      q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; q[3] = bits(oct.parent[i]);
+      q[4] = b[3]; q[5] = b[4]; q[6] = b[5];
+    }
+    hb.oct_face_off = std::move(oct.face_off);
+    hb.oct_face_leaf = std::move(oct.face_leaf);
+  }
+  if (S > 0) {
+    hb.spheres.assign(desc->spheres, desc->spheres + (size_t)S * 4);
+    hb.sphere_mat.assign(desc->sphere_material, desc->sphere_material + S);
+  }
+  hb.proto.n_faces = T; hb.proto.n_spheres = S; hb.proto.n_prims = N; hb.proto.n_nodes = (int32_t)hb.nodes.size();
+  hb.bake_ms = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_start).count();
+}
+
+// Upload a baked scene to the CURRENT device (use_device) and create its per-frame workspace.
+int upload_scene(const HostBake &hb, RtScene **out) {
+  const auto t_start = std::chrono::high_resolution_clock::now();
+  RtScene *sc = new RtScene();
+  sc->device = g_device;
+  sc->dev = hb.proto;
+  sc->h_nodes = hb.nodes;
+  sc->h_prim_face = hb.prim_face;
+  sc->n_leaves = hb.n_leaves;
+  sc->bvh_depth = hb.bvh_depth;
+  sc->octree_ms = hb.octree_ms;
+  memcpy(sc->oct_stats, hb.oct_stats, sizeof(hb.oct_stats));
+  int rc;
+  if ((rc = upload(sc->nodes, hb.nodes.data(), hb.nodes.size() * sizeof(rt::PairNode))) ||
+      (rc = upload(sc->prims, hb.prims.data(), hb.prims.size() * 4)) ||
+      (rc = upload(sc->shade, hb.shade.data(), hb.shade.size() * 4)) ||
+      (rc = upload(sc->mats, hb.mats.data(), hb.mats.size() * 4)) ||
+      (rc = upload(sc->spheres, hb.spheres.data(), hb.spheres.size() * 4)) ||
+      (rc = upload(sc->sphere_mat, hb.sphere_mat.data(), hb.sphere_mat.size() * 4)) ||
+      (hb.use_filter && ((rc = upload(sc->oct_box, hb.oct_packed.data(), hb.oct_packed.size() * 4)) ||
+                         (rc = upload(sc->oct_face_off, hb.oct_face_off.data(), hb.oct_face_off.size() * 4)) ||
+                         (rc = upload(sc->oct_face_leaf, hb.oct_face_leaf.data(), hb.oct_face_leaf.size() * 4)))) ||
       (rc = sc->frame_counts.reserve(sizeof(FrameCounts))) || (rc = sc->frame_params.reserve(sizeof(FrameParams)))) {
     rt_scene_destroy(sc);
     return rc;
@@ -495,14 +613,54 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
   sc->dev.mats = sc->mats.as<float4>();
   sc->dev.spheres = sc->spheres.as<float4>();
   sc->dev.sphere_mat = sc->sphere_mat.as<int32_t>();
-  sc->dev.n_faces = T; sc->dev.n_spheres = S; sc->dev.n_prims = N; sc->dev.n_nodes = (int32_t)bvh.nodes.size();
-  sc->build_ms = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_start).count();
+  if (hb.use_filter) {
+    sc->dev.oct_box = sc->oct_box.as<float4>();
+    sc->dev.oct_face_off = sc->oct_face_off.as<int32_t>();
+    sc->dev.oct_face_leaf = sc->oct_face_leaf.as<int32_t>();
+  }
+  sc->build_ms = hb.bake_ms + std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_start).count();
+  {
+    std::lock_guard<std::mutex> lk(g_scenes_mu);
+    g_scenes.push_back(sc);
+  }
   *out = sc;
   return RT_OK;
 }
 
+}  // namespace
+
+extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
+  if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
+  int rc = validate_scene_desc(desc);
+  if (rc) return rc;
+  if ((rc = ensure_device())) return rc;
+  HostBake hb;
+  bake_scene(desc, hb);
+  return upload_scene(hb, out);
+}
+
+namespace {
+void release_workspace(RtScene *sc) {
+  if (use_device(sc->device)) return;
+  cudaDeviceSynchronize();
+  for (auto &l : sc->levels) l.release();
+  sc->levels.clear();
+  if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
+  sc->graph_key.clear();
+  sc->fq_o.release(); sc->fq_d.release(); sc->fq_x.release(); sc->frec_a.release(); sc->frec_b.release();
+  for (int k = 0; k < 2; ++k) { sc->slot_rgba[k].release(); sc->slot_busy[k] = false; }
+  sc->out_rgba.release(); sc->out_face.release(); sc->out_t.release(); sc->out_rgbf.release();
+  sc->in_a.release(); sc->in_b.release();
+}
+}  // namespace
+
 extern "C" void rt_scene_destroy(RtScene *sc) {
   if (!sc) return;
+  {
+    std::lock_guard<std::mutex> lk(g_scenes_mu);
+    g_scenes.erase(std::remove(g_scenes.begin(), g_scenes.end(), sc), g_scenes.end());
+  }
+  use_device(sc->device);
   sc->nodes.release(); sc->prims.release(); sc->shade.release(); sc->mats.release();
   sc->spheres.release(); sc->sphere_mat.release();
   sc->oct_box.release(); sc->oct_face_off.release(); sc->oct_face_leaf.release();
@@ -782,12 +940,30 @@ struct EventTimer {
 };
 
 template <class K>
+int persistent_grid(K kernel, int block);
+
+// Persistent grid sizes of the current device, recomputed when "persistent_ctas_per_sm" changes
+const DeviceState &device_grids();
+
+template <class K>
 int persistent_grid(K kernel, int block) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
   if (per_sm < 1) per_sm = 1;
   if (g_opt_ctas_per_sm > 0) per_sm = std::min(per_sm, g_opt_ctas_per_sm);
   return per_sm * std::max(1, g_sm_count);
+}
+
+const DeviceState &device_grids() {
+  DeviceState &d = g_devs[g_device];
+  if (d.grids_opt != g_opt_ctas_per_sm) {
+    d.g1p = persistent_grid(k_trace_nearest<true, false>, 128); d.g1s = persistent_grid(k_trace_nearest<false, false>, 128);
+    d.g2 = persistent_grid(k_shadow<false>, 128); d.g1ps = persistent_grid(k_trace_nearest<true, true>, 128);
+    d.g1ss = persistent_grid(k_trace_nearest<false, true>, 128); d.g2s = persistent_grid(k_shadow<true>, 128);
+    d.kf = persistent_grid(k_frame<false>, 128); d.kfs = persistent_grid(k_frame<true>, 128);
+    d.grids_opt = g_opt_ctas_per_sm;
+  }
+  return d;
 }
 
 // Runs the wavefront pipeline.  Level 0 is either generated from the camera (n0 = local pixels)
@@ -819,15 +995,8 @@ void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, con
 int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *launches) {
   const FrameParams *fpp = sc->frame_params.as<FrameParams>();
   FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
-  static int grid_k1p = 0, grid_k1s = 0, grid_k2 = 0, grid_k1p_s = 0, grid_k1s_s = 0, grid_k2_s = 0;
-  if (!grid_k1p) {
-    grid_k1p = persistent_grid(k_trace_nearest<true, false>, 128);
-    grid_k1s = persistent_grid(k_trace_nearest<false, false>, 128);
-    grid_k2 = persistent_grid(k_shadow<false>, 128);
-    grid_k1p_s = persistent_grid(k_trace_nearest<true, true>, 128);
-    grid_k1s_s = persistent_grid(k_trace_nearest<false, true>, 128);
-    grid_k2_s = persistent_grid(k_shadow<true>, 128);
-  }
+  const DeviceState &G = device_grids();
+  const int grid_k1p = G.g1p, grid_k1s = G.g1s, grid_k2 = G.g2, grid_k1p_s = G.g1ps, grid_k1s_s = G.g1ss, grid_k2_s = G.g2s;
   const int elem_blocks = std::max(1, std::min((pl.n0 + 127) / 128, g_sm_count * 16));
   CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
   for (int level = 0; level <= pl.depth_cap; ++level) {
@@ -866,12 +1035,8 @@ int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *
 int enqueue_level(RtScene *sc, const FramePlan &pl, cudaStream_t cs, int level, cudaGraphConditionalHandle next_cond) {
   const FrameParams *fpp = sc->frame_params.as<FrameParams>();
   FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
-  static int g1p = 0, g1s = 0, g2 = 0, g1ps = 0, g1ss = 0, g2s = 0;
-  if (!g1p) {
-    g1p = persistent_grid(k_trace_nearest<true, false>, 128); g1s = persistent_grid(k_trace_nearest<false, false>, 128);
-    g2 = persistent_grid(k_shadow<false>, 128); g1ps = persistent_grid(k_trace_nearest<true, true>, 128);
-    g1ss = persistent_grid(k_trace_nearest<false, true>, 128); g2s = persistent_grid(k_shadow<true>, 128);
-  }
+  const DeviceState &G = device_grids();
+  const int g1p = G.g1p, g1s = G.g1s, g2 = G.g2, g1ps = G.g1ps, g1ss = G.g1ss, g2s = G.g2s;
   const int elem_blocks = std::max(1, std::min((pl.n0 + 127) / 128, g_sm_count * 16));
   LevelBufs lv = sc->levels[level].bufs();
   LevelBufs nx = sc->levels[level + 1].bufs();
@@ -1002,14 +1167,7 @@ int fused_reserve(RtScene *sc, size_t n0, int depth_cap) {
 }
 
 template <bool STATS>
-int fused_grid() {
-  static int cached_opt = -1, cached_dev = -1, cached = 0;
-  if (cached_opt != g_opt_ctas_per_sm || cached_dev != g_device) {
-    cached = persistent_grid(k_frame<STATS>, 128);
-    cached_opt = g_opt_ctas_per_sm; cached_dev = g_device;
-  }
-  return cached;
-}
+int fused_grid() { return STATS ? device_grids().kfs : device_grids().kf; }
 
 int run_fused(RtScene *sc, FrameParams &fp, bool explicit_rays, int n0, cudaStream_t st, bool own_stream, RtStats *stats) {
   FusedShape sh;
@@ -1121,7 +1279,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
     for (int l = 0; l <= pl.depth_cap; ++l)
       if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
-    const std::vector<long long> key = {g_alloc_generation, n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, g_opt_graph_cond,
+    const std::vector<long long> key = {g_alloc_generation.load(), n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, g_opt_graph_cond, g_opt_ctas_per_sm,
                                         (long long)pl.explicit_rays, (long long)pl.trav_stats};
     if (sc->graph_exec == nullptr || key != sc->graph_key) {
       if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
@@ -1157,12 +1315,8 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((rc = sc->levels[0].reserve((size_t)n0, (size_t)pl.J))) return rc;
   }
   CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
-  static int g1p = 0, g1s = 0, g2 = 0, g1ps = 0, g1ss = 0, g2s = 0;
-  if (!g1p) {
-    g1p = persistent_grid(k_trace_nearest<true, false>, 128); g1s = persistent_grid(k_trace_nearest<false, false>, 128);
-    g2 = persistent_grid(k_shadow<false>, 128); g1ps = persistent_grid(k_trace_nearest<true, true>, 128);
-    g1ss = persistent_grid(k_trace_nearest<false, true>, 128); g2s = persistent_grid(k_shadow<true>, 128);
-  }
+  const DeviceState &G = device_grids();
+  const int g1p = G.g1p, g1s = G.g1s, g2 = G.g2, g1ps = G.g1ps, g1ss = G.g1ss, g2s = G.g2s;
   const int elem_blocks = std::max(1, std::min((n0 + 127) / 128, g_sm_count * 16));
   int levels_run = 0;
   int cur_n = n0;  // host knowledge of the level's ray count (exact in sync mode, upper bound in async mode)
@@ -1252,7 +1406,7 @@ extern "C" int rt_render_device(RtScene *sc, const RtCamera *cam, const RtLights
   if (!sc || !cam || !lights || !p || !d_rgba) return fail(RT_ERR_INVALID, "null argument");
   if (p->width <= 0 || p->height <= 0) return fail(RT_ERR_INVALID, "bad image size %dx%d", p->width, p->height);
   if (p->band_world > 1 && (p->band_rank < 0 || p->band_rank >= p->band_world)) return fail(RT_ERR_INVALID, "bad band rank");
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   FrameParams fp;
   if ((rc = fill_frame(fp, cam, lights, p))) return rc;
@@ -1265,7 +1419,7 @@ extern "C" int rt_render_device(RtScene *sc, const RtCamera *cam, const RtLights
 extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *lights, const RtParams *p, uint8_t *rgba_out,
                          int32_t *face_out, float *t_out, float *rgb_f32_out, RtStats *stats) {
   if (!sc || !p || !rgba_out) return fail(RT_ERR_INVALID, "null argument");
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   const size_t n = (size_t)rt_local_rows(p) * (size_t)std::max(0, p->width);
   if ((rc = sc->out_rgba.reserve(n * 4))) return rc;
@@ -1293,7 +1447,7 @@ extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *light
 extern "C" int rt_render_submit(RtScene *sc, const RtCamera *cam, const RtLights *lights, const RtParams *p,
                                 uint8_t *rgba_out, int *ticket) {
   if (!sc || !p || !rgba_out || !ticket) return fail(RT_ERR_INVALID, "null argument");
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   const int slot = sc->submit_seq & 1;
   if (sc->slot_busy[slot])
@@ -1320,6 +1474,7 @@ extern "C" int rt_render_submit(RtScene *sc, const RtCamera *cam, const RtLights
 
 extern "C" int rt_render_wait(RtScene *sc, int ticket) {
   if (!sc) return fail(RT_ERR_INVALID, "null scene");
+  if (use_device(sc->device)) return RT_ERR_NO_DEVICE;
   if (ticket < 0 || ticket >= sc->submit_seq) return fail(RT_ERR_INVALID, "unknown ticket %d", ticket);
   if (ticket < sc->submit_seq - 2 || !sc->slot_busy[ticket & 1]) return RT_OK;  // already complete
   if (ticket == sc->submit_seq - 1 && sc->slot_busy[(ticket & 1) ^ 1]) {
@@ -1341,7 +1496,10 @@ extern "C" int rt_shared_frame_create(size_t bytes, void **d_ptr, unsigned char 
   int rc = ensure_device();
   if (rc) return rc;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  CUDA_TRY(cudaMalloc(d_ptr, bytes));
+  // the frame, then 4 KiB of per-rank completion flags (rt_shared_frame_signal / rt_shared_frame_wait)
+  const size_t frame_al = (bytes + 255) & ~(size_t)255;
+  CUDA_TRY(cudaMalloc(d_ptr, frame_al + 4096));
+  CUDA_TRY(cudaMemset((char *)*d_ptr + frame_al, 0, 4096));
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
   if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return fail(RT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
@@ -1380,7 +1538,7 @@ extern "C" int rt_trace_rays(RtScene *sc, int64_t n, const float *origins, const
   if (!sc || !origins || !dirs || !lights || !p || !rgb_out) return fail(RT_ERR_INVALID, "null argument");
   if (n <= 0) return RT_OK;
   if (n > (1 << 26)) return fail(RT_ERR_LIMIT, "at most 2^26 rays per call");
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   FrameParams fp;
   if ((rc = fill_frame(fp, nullptr, lights, p))) return rc;
@@ -1426,7 +1584,7 @@ extern "C" int rt_trace_rays(RtScene *sc, int64_t n, const float *origins, const
 extern "C" int rt_light_strikes(RtScene *sc, int64_t n, const float *hit_points, const RtLights *lights, uint8_t *visible_out) {
   if (!sc || !hit_points || !lights || !visible_out) return fail(RT_ERR_INVALID, "null argument");
   if (n <= 0 || lights->n <= 0) return RT_OK;
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   RtParams p; rt_default_params(&p);
   FrameParams fp;
@@ -1444,7 +1602,7 @@ extern "C" int rt_light_strikes(RtScene *sc, int64_t n, const float *hit_points,
 extern "C" int rt_box_intersect(RtScene *sc, int64_t n, const float *origins, const float *dests, uint8_t *hit_out) {
   if (!sc || !origins || !dests || !hit_out) return fail(RT_ERR_INVALID, "null argument");
   if (n <= 0) return RT_OK;
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   if ((rc = sc->in_a.reserve((size_t)n * 24)) || (rc = sc->in_b.reserve((size_t)n))) return rc;
   float *d_o = sc->in_a.as<float>(), *d_d = d_o + (size_t)n * 3;
@@ -1481,7 +1639,7 @@ extern "C" int rt_ray_triangle(RtScene *sc, int64_t n, const float *origins, con
                                float *t_out) {
   if (!sc || !origins || !dirs || !faces || !t_out) return fail(RT_ERR_INVALID, "null argument");
   if (n <= 0) return RT_OK;
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   if ((rc = sc->in_a.reserve((size_t)n * 28)) || (rc = sc->in_b.reserve((size_t)n * 4))) return rc;
   float *d_o = sc->in_a.as<float>(), *d_d = d_o + (size_t)n * 3;
@@ -1498,7 +1656,7 @@ extern "C" int rt_ray_triangle(RtScene *sc, int64_t n, const float *origins, con
 
 extern "C" int rt_octree_candidates(RtScene *sc, const float origin[3], const float dest[3], int32_t *ids, int32_t cap) {
   if (!sc || !origin || !dest || (!ids && cap > 0)) return fail(RT_ERR_INVALID, "null argument");
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   const int T = sc->dev.n_faces;
   if (T == 0) return 0;
@@ -1519,7 +1677,7 @@ extern "C" int rt_phong_shade(RtScene *sc, int64_t n, const float *origins, cons
                               const RtLights *lights, const RtParams *p, float *rgb_out) {
   if (!sc || !origins || !hit_points || !faces || !lights || !p || !rgb_out) return fail(RT_ERR_INVALID, "null argument");
   if (n <= 0) return RT_OK;
-  int rc = ensure_device();
+  int rc = use_device(sc->device);
   if (rc) return rc;
   FrameParams fp;
   if ((rc = fill_frame(fp, nullptr, lights, p))) return rc;
@@ -1650,3 +1808,5 @@ extern "C" int rt_write_ppm(const char *path, const uint8_t *rgba, int32_t width
   fclose(f);
   return RT_OK;
 }
+
+#include "rt_multi.inl"

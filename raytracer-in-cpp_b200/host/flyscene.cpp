@@ -29,8 +29,14 @@ bool BoundingBox::boxIntersect(const Vector3f &origin, const Vector3f &dest) {
 // BoxTree
 // ---------------------------------------------------------------------------------------------
 BoxTree::BoxTree(const RtSceneDesc &scene, int cap) {
-  capacity = cap;
   check(rt_scene_create(&scene, &scene_), "BoxTree::BoxTree");
+  describe(scene, cap);
+}
+
+BoxTree::BoxTree(const RtSceneDesc &scene, int cap, RtScene *borrowed) : scene_(borrowed), owns_(false) { describe(scene, cap); }
+
+void BoxTree::describe(const RtSceneDesc &scene, int cap) {
+  capacity = cap;
   float mn[3], mx[3];
   rt_scene_root_box(scene_, mn, mx);
   box = BoundingBox(Vector3f(mn), Vector3f(mx));
@@ -44,14 +50,15 @@ BoxTree::BoxTree(const RtSceneDesc &scene, int cap) {
 }
 
 BoxTree::~BoxTree() {
-  if (scene_) rt_scene_destroy(scene_);
+  if (scene_ && owns_) rt_scene_destroy(scene_);
 }
 
 BoxTree::BoxTree(BoxTree &&o) noexcept { *this = std::move(o); }
 
 BoxTree &BoxTree::operator=(BoxTree &&o) noexcept {
   if (this != &o) {
-    if (scene_) rt_scene_destroy(scene_);
+    if (scene_ && owns_) rt_scene_destroy(scene_);
+    owns_ = o.owns_;
     box = o.box; capacity = o.capacity; isLeaf = o.isLeaf; isEmpty = o.isEmpty;
     faces = std::move(o.faces);
     oct_stats = std::move(o.oct_stats);
@@ -166,6 +173,8 @@ Vector3f Flycamera::screenToWorld(float i, float j) const {
 // Flyscene
 // ---------------------------------------------------------------------------------------------
 Flyscene::~Flyscene() {
+  octree = BoxTree();  // drop the (possibly borrowed) view before the scenes it points into
+  if (multi) rt_multi_destroy(multi);
   if (mesh) rt_mesh_destroy(mesh);
 }
 
@@ -188,7 +197,16 @@ void Flyscene::initialize(int width, int height) {
   lights.push_back(Vector3f(-1.0f, 1.0f, 1.0f));  // :72
   std::cout << "Seting up acceleration data structure ..." << std::endl;
   const auto t0 = std::chrono::high_resolution_clock::now();
-  octree = BoxTree(desc, 1000);  // :86,93
+  if (devices.size() > 1) {
+    // one scene per GPU, baked once; `octree` views the first device's copy
+    check(rt_multi_create(&desc, (int)devices.size(), devices.data(), &multi), "rt_multi_create");
+    RtScene *first = nullptr;
+    check(rt_multi_scene(multi, 0, &first), "rt_multi_scene");
+    octree = BoxTree(desc, 1000, first);
+  } else {
+    if (devices.size() == 1) check(rt_init(devices[0]), "rt_init");
+    octree = BoxTree(desc, 1000);  // :86,93
+  }
   octree_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
   std::cout << "Seting up acceleration data structure: done!\nELAPSED TIME:" << octree_seconds << std::endl;
 }
@@ -226,7 +244,8 @@ const std::vector<uint8_t> &Flyscene::render(int width, int height, RtStats *sta
   memcpy(L.color, light_color, sizeof(light_color));
   const RtParams p = params(width, height);
   frame.assign((size_t)width * height * 4, 0);
-  check(rt_render(octree.handle(), &cam, &L, &p, frame.data(), nullptr, nullptr, nullptr, stats), "raytraceScene");
+  if (multi) check(rt_multi_render(multi, &cam, &L, &p, frame.data(), stats), "raytraceScene");
+  else check(rt_render(octree.handle(), &cam, &L, &p, frame.data(), nullptr, nullptr, nullptr, stats), "raytraceScene");
   return frame;
 }
 

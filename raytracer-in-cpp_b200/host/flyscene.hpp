@@ -68,6 +68,8 @@ class BoxTree {
   BoxTree() {}
   // builds BVH + candidate filter from a baked scene description and uploads it (rt_scene_create)
   BoxTree(const RtSceneDesc &scene, int capacity);
+  // the same view over a scene that somebody else owns (device 0 of a multi-GPU scene, rt_multi_scene)
+  BoxTree(const RtSceneDesc &scene, int capacity, RtScene *borrowed);
   ~BoxTree();
   BoxTree(BoxTree &&o) noexcept;
   BoxTree &operator=(BoxTree &&o) noexcept;
@@ -81,7 +83,9 @@ class BoxTree {
   RtScene *handle() const { return scene_; }
 
  private:
+  void describe(const RtSceneDesc &scene, int cap);
   RtScene *scene_ = nullptr;
+  bool owns_ = true;
   std::vector<int64_t> oct_stats;
 };
 
@@ -160,6 +164,10 @@ class Flyscene {
   void setMaxDepth(int d) { max_depth = d; }
   void setAreaGrid(int u, int v) { usteps = u; vsteps = v; }
   void setSphereSeed(uint32_t s) { sphere_seed = s; }  // spherical light mode: RtParams.sphere_seed
+  // GPUs of this box that raytraceScene() spreads the image over (interleaved row bands, rt_multi_*): the role
+  // of the reference's ThreadPool workers (src/flyscene.cpp:558,609).  Call before initialize(); default: the
+  // device chosen by rt_init.
+  void setDevices(const std::vector<int> &d) { devices = d; }
 
   Flycamera *getCamera() { return &flycamera; }
   void addLight() { lights.push_back(flycamera.getCenter()); }
@@ -193,6 +201,8 @@ class Flyscene {
   Flycamera flycamera;
   std::vector<Vector3f> lights;
   RtMesh *mesh = nullptr;
+  RtMulti *multi = nullptr;  // more than one device: the scenes of all devices (octree views device 0's)
+  std::vector<int> devices;
   RtSceneDesc desc{};
   std::string model_path = "resources/models/cube.obj";  // src/flyscene.cpp:51
   bool areaLight = false, pointLight = true, mode_set = false;

@@ -4,7 +4,7 @@
 //
 //   rt_cli [--scene file.obj] [--width W] [--height H] [--area 0|1] [--point 0|1]
 //          [--max-depth D] [--grid U V] [--light x y z]... [--cam-rot rx ry] [--cam-trans x y z]
-//          [--frames N] [--device k]
+//          [--frames N] [--device k] [--gpus N]      (--gpus N: devices 0..N-1 share every frame, rt_multi_*)
 // Without --area/--point the two flags are read from stdin exactly like the reference.
 #include <cstdio>
 #include <cstdlib>
@@ -17,7 +17,7 @@
 
 int main(int argc, char **argv) {
   std::string scene = "resources/models/cube.obj";
-  int W = 1000, H = 1000, area = -1, point = -1, depth = -1, gu = 5, gv = 5, frames = 1, device = 0;
+  int W = 1000, H = 1000, area = -1, point = -1, depth = -1, gu = 5, gv = 5, frames = 1, device = 0, gpus = 1;
   float rx = 0, ry = 0, tx = 0, ty = 0, tz = 0;
   uint32_t sphere_seed = 1;
   std::vector<rt::Vector3f> extra_lights;
@@ -39,6 +39,7 @@ int main(int argc, char **argv) {
     else if (a == "--cam-trans") { tx = atof(next()); ty = atof(next()); tz = atof(next()); }
     else if (a == "--frames") frames = atoi(next());
     else if (a == "--device") device = atoi(next());
+    else if (a == "--gpus") gpus = atoi(next());
     else if (a == "--sphere-seed") sphere_seed = (uint32_t)strtoul(next(), nullptr, 10);
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
   }
@@ -50,6 +51,11 @@ int main(int argc, char **argv) {
     fs.setMaxDepth(depth);
     fs.setAreaGrid(gu, gv);
     fs.setSphereSeed(sphere_seed);
+    if (gpus > 1) {
+      std::vector<int> devs;
+      for (int k = 0; k < gpus; ++k) devs.push_back(device + k);
+      fs.setDevices(devs);
+    }
     fs.initialize(W, H);
     for (const auto &l : extra_lights) fs.getLights().push_back(l);
     if (rx != 0 || ry != 0) fs.getCamera()->setRotation(rx, ry);
@@ -57,8 +63,8 @@ int main(int argc, char **argv) {
     for (int f = 0; f < frames; ++f) fs.raytraceScene();
     RtStats st;
     fs.render(W, H, &st);
-    printf("{\"faces\": %d, \"octree_build_s\": %.6f, \"frame_ms\": %.4f, \"rays\": %lld, \"mrays_per_s\": %.2f}\n",
-           fs.getNumberOfFaces(), fs.octree_seconds, st.ms_total,
+    printf("{\"faces\": %d, \"gpus\": %d, \"octree_build_s\": %.6f, \"frame_ms\": %.4f, \"rays\": %lld, \"mrays_per_s\": %.2f}\n",
+           fs.getNumberOfFaces(), gpus, fs.octree_seconds, st.ms_total,
            (long long)(st.rays_primary + st.rays_shadow + st.rays_secondary),
            (st.rays_primary + st.rays_shadow + st.rays_secondary) / (st.ms_total * 1e3));
   } catch (const std::exception &e) {

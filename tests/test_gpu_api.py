@@ -434,3 +434,79 @@ def test_scenes_that_fit_one_leaf(n_tri, leaf, pkg, oracle_mod):
     err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - np.clip(O.quantize(rgb), 0, 255)).max(-1)
     assert err.max() <= 1 and (err == 0).mean() > 0.999
     scene.close()
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0], [0, 1], [0, 1, 2, 3]])
+def test_multi_gpu_frame_equals_single_gpu_frame(devices, pkg, scene_dir):
+    """rt_multi_*: one host process, one worker thread per device, interleaved row bands.  The host frame (every
+    device copies its own bands into it) and the device frame (kernels store into device 0's frame over peer
+    access) must both equal the single-GPU frame byte for byte.  Listing device 0 several times runs the same
+    band split on one GPU (what a single-GPU box can check); real device lists need that many GPUs."""
+    if max(devices) >= _n_gpus():
+        pytest.skip(f"needs {max(devices) + 1} GPUs")
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("gallery_area_200x150")
+    arrs = (g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    W, H = 333, 187   # odd sizes: partial tiles and a partial last band
+    cam = capi.default_camera(W, H)
+    lights = capi.Lights(g["lights"][:1], g["light_color"])
+    single = capi.Scene(*arrs, g["model_matrix"])
+    for (area, point, depth, grid, band_rows) in [(1, 0, 3, (4, 4), 0), (0, 1, -1, (5, 5), 8), (1, 0, 2, (3, 3), 24)]:
+        params = capi.make_params(W, H, area, point, depth, grid)
+        ref = single.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False).rgba
+        multi = capi.Multi(devices, *arrs, g["model_matrix"])
+        params.band_rows = band_rows
+        out, st = multi.render(cam, lights, params, want_stats=True)
+        assert (out == ref).all(), f"host frame of {devices} differs from the single-GPU frame"
+        assert st["rays_primary"] == W * H
+        out2 = multi.render(cam, lights, params)       # the timed path (no stats)
+        assert (out2 == ref).all()
+        ptr, ms = multi.render_device(cam, lights, params)
+        dev = np.zeros((H, W, 4), np.uint8)
+        assert capi.lib().rt_device_copy_to_host(dev.ctypes.data, ptr, dev.nbytes) == 0
+        assert (dev == ref).all(), f"device-resident frame of {devices} differs"
+        assert ms > 0
+        multi.close()
+    single.close()
+
+
+def test_render_into_frame_assembles_bands_on_the_host(pkg):
+    """rt_render_into_frame (what each per-GPU process of a torchrun job calls): 3 emulated ranks copy their own
+    bands into one host frame; the result equals rt_render's frame."""
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("cube_point_1000")
+    scene = capi.Scene(g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    W, H = 320, 203
+    cam = capi.default_camera(W, H)
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    ref = scene.render(cam, lights, capi.make_params(W, H, 1, 0, 3, (4, 4)), want_face=False, want_t=False, want_rgb=False).rgba
+    frame = np.zeros((H, W, 4), np.uint8)
+    for world, rows in [(3, 8), (2, 16), (1, 8)]:
+        frame[:] = 0
+        for r in range(world):
+            scene.render_into_frame(cam, lights, capi.make_params(W, H, 1, 0, 3, (4, 4), rows, r, world), frame.ctypes.data)
+        assert (frame == ref).all(), (world, rows)
+    scene.close()
+
+
+def test_shutdown_releases_workspaces_and_scenes_stay_usable(pkg):
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("cube_point_1000")
+    scene = capi.Scene(g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    cam = capi.default_camera(160, 90)
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    params = capi.make_params(160, 90, 1, 0, 3, (4, 4))
+    a = scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False).rgba
+    capi.lib().rt_shutdown()
+    capi.init(0)
+    b = scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False).rgba
+    assert (a == b).all()
+    scene.close()
