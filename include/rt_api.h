@@ -162,8 +162,9 @@ int rt_device_name(char *buf, size_t n);
  * reference's octree candidate sets so that the image matches the reference bit for bit; 0: plain
  * BVH = exact nearest hit over all faces), "graph_conditionals" (1, default: empty bounce levels are skipped inside the frame's CUDA graph),
  * "fused_frame" (the frame as one persistent kernel, csrc/rt_frame.cuh: 0 never, 1 whenever eligible, 2 = default:
- *   for frames of at most "fused_max_kpixels" thousand rays (default 1200) and for unbounded depth; larger frames
- *   take the per-level wavefront kernels of csrc/rt_kernels.cuh -- both paths give bit-identical frames),
+ *   for scenes without spheres and without an octree filter (<= 1000 triangles, e.g. the bundled cube), for frames of
+ *   at most "fused_max_kpixels" thousand rays (default 1200) and for unbounded depth; other frames take the
+ *   per-level wavefront kernels of csrc/rt_kernels.cuh -- both paths give bit-identical frames),
  * "continue_min_lanes" (fused frame: child rays stay in their warp when at least this many of its lanes spawned one; default 8) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);

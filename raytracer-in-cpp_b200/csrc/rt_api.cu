@@ -43,7 +43,8 @@ thread_local int g_sm_count = 0;
 struct DeviceState {
   int sm_count = 0;
   int grids_opt = -1;  // value of persistent_ctas_per_sm the grids below were computed for
-  int g1p = 0, g1s = 0, g2 = 0, g1ps = 0, g1ss = 0, g2s = 0, kf = 0, kfs = 0;  // persistent grid sizes
+  // persistent grid sizes: [primary rays?][stats build?][plain scene?]
+  int g_trace[2][2][2] = {}, g_shadow[2][2] = {}, g_frame[2][2] = {};
 };
 constexpr int kMaxDevices = 64;
 DeviceState g_devs[kMaxDevices];
@@ -555,6 +556,23 @@ void bake_scene(const RtSceneDesc *desc, HostBake &hb) {
   }
 
   hb.nodes = std::move(bvh.nodes);
+  {
+    // bounds of everything the BVH holds = union of the root pair's two child boxes (segment_reaches_bvh)
+    const float inf = std::numeric_limits<float>::infinity();
+    float bmn[3] = {inf, inf, inf}, bmx[3] = {-inf, -inf, -inf};
+    if (N > 0 && !hb.nodes.empty()) {
+      const rt::PairNode &r = hb.nodes[0];
+      for (int c = 0; c < 2; ++c) {
+        int32_t code;
+        memcpy(&code, &r.q[12 + c], 4);
+        if (code == rt::kEmptyLeaf) continue;
+        const float mn[3] = {r.q[4 * c + 0], r.q[4 * c + 2], r.q[8 + 2 * c]}, mx[3] = {r.q[4 * c + 1], r.q[4 * c + 3], r.q[9 + 2 * c]};
+        for (int a = 0; a < 3; ++a) { bmn[a] = std::min(bmn[a], mn[a]); bmx[a] = std::max(bmx[a], mx[a]); }
+      }
+    }
+    memcpy(hb.proto.bvh_min, bmn, 12);
+    memcpy(hb.proto.bvh_max, bmx, 12);
+  }
   if (use_filter) {
     const int n = oct.n_nodes();
     hb.oct_packed.assign((size_t)n * 8, 0.f);
@@ -957,10 +975,18 @@ int persistent_grid(K kernel, int block) {
 const DeviceState &device_grids() {
   DeviceState &d = g_devs[g_device];
   if (d.grids_opt != g_opt_ctas_per_sm) {
-    d.g1p = persistent_grid(k_trace_nearest<true, false>, 128); d.g1s = persistent_grid(k_trace_nearest<false, false>, 128);
-    d.g2 = persistent_grid(k_shadow<false>, 128); d.g1ps = persistent_grid(k_trace_nearest<true, true>, 128);
-    d.g1ss = persistent_grid(k_trace_nearest<false, true>, 128); d.g2s = persistent_grid(k_shadow<true>, 128);
-    d.kf = persistent_grid(k_frame<false>, 128); d.kfs = persistent_grid(k_frame<true>, 128);
+    d.g_trace[0][0][0] = persistent_grid(k_trace_nearest<false, false, false>, 128);
+    d.g_trace[0][0][1] = persistent_grid(k_trace_nearest<false, false, true>, 128);
+    d.g_trace[0][1][0] = persistent_grid(k_trace_nearest<false, true, false>, 128);
+    d.g_trace[0][1][1] = persistent_grid(k_trace_nearest<false, true, true>, 128);
+    d.g_trace[1][0][0] = persistent_grid(k_trace_nearest<true, false, false>, 128);
+    d.g_trace[1][0][1] = persistent_grid(k_trace_nearest<true, false, true>, 128);
+    d.g_trace[1][1][0] = persistent_grid(k_trace_nearest<true, true, false>, 128);
+    d.g_trace[1][1][1] = persistent_grid(k_trace_nearest<true, true, true>, 128);
+    d.g_shadow[0][0] = persistent_grid(k_shadow<false, false>, 128); d.g_shadow[0][1] = persistent_grid(k_shadow<false, true>, 128);
+    d.g_shadow[1][0] = persistent_grid(k_shadow<true, false>, 128); d.g_shadow[1][1] = persistent_grid(k_shadow<true, true>, 128);
+    d.g_frame[0][0] = persistent_grid(k_frame<false, false>, 128); d.g_frame[0][1] = persistent_grid(k_frame<false, true>, 128);
+    d.g_frame[1][0] = persistent_grid(k_frame<true, false>, 128); d.g_frame[1][1] = persistent_grid(k_frame<true, true>, 128);
     d.grids_opt = g_opt_ctas_per_sm;
   }
   return d;
@@ -983,11 +1009,34 @@ struct FramePlan {
   int n0, J, Lmax, S, depth_cap;
 };
 
+// A scene without analytic spheres and without an octree candidate filter runs the PLAIN kernel variants
+bool scene_is_plain(const RtScene *sc) { return sc->dev.n_spheres == 0 && sc->dev.oct_box == nullptr; }
+
+// K1 for one level: nearest hit of the primary rays (generated in-kernel) or of the queued rays
+void launch_trace(RtScene *sc, bool primary, bool stats, const FrameParams *fpp, const LevelBufs &lv, int level, int n_param,
+                  FrameCounts *fc, cudaStream_t st) {
+  const bool plain = scene_is_plain(sc);
+  const int grid = device_grids().g_trace[primary][stats][plain];
+#define RT_K1(PRIM_, STATS_, PLAIN_) k_trace_nearest<PRIM_, STATS_, PLAIN_><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc)
+  if (primary) {
+    if (stats) { if (plain) RT_K1(true, true, true); else RT_K1(true, true, false); }
+    else { if (plain) RT_K1(true, false, true); else RT_K1(true, false, false); }
+  } else {
+    if (stats) { if (plain) RT_K1(false, true, true); else RT_K1(false, true, false); }
+    else { if (plain) RT_K1(false, false, true); else RT_K1(false, false, false); }
+  }
+#undef RT_K1
+}
+
 // K2 for one level: gate + sample rays of every hit
 void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, const LevelBufs &lv, int level, FrameCounts *fc,
-                   cudaStream_t st, int grid, int *launches) {
-  if (pl.trav_stats) k_shadow<true><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc);
-  else k_shadow<false><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc);
+                   cudaStream_t st, int *launches) {
+  const bool plain = scene_is_plain(sc);
+  const int grid = device_grids().g_shadow[pl.trav_stats][plain];
+#define RT_K2(STATS_, PLAIN_) k_shadow<STATS_, PLAIN_><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc)
+  if (pl.trav_stats) { if (plain) RT_K2(true, true); else RT_K2(true, false); }
+  else { if (plain) RT_K2(false, true); else RT_K2(false, false); }
+#undef RT_K2
   *launches += 1;
 }
 
@@ -995,22 +1044,14 @@ void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, con
 int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *launches) {
   const FrameParams *fpp = sc->frame_params.as<FrameParams>();
   FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
-  const DeviceState &G = device_grids();
-  const int grid_k1p = G.g1p, grid_k1s = G.g1s, grid_k2 = G.g2, grid_k1p_s = G.g1ps, grid_k1s_s = G.g1ss, grid_k2_s = G.g2s;
   const int elem_blocks = std::max(1, std::min((pl.n0 + 127) / 128, g_sm_count * 16));
   CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
   for (int level = 0; level <= pl.depth_cap; ++level) {
     LevelBufs lv = sc->levels[level].bufs();
     LevelBufs nx = sc->levels[level + 1].bufs();
     const int n_param = level == 0 ? pl.n0 : -1;
-    if (level == 0 && !pl.explicit_rays) {
-      if (pl.trav_stats) k_trace_nearest<true, true><<<grid_k1p_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-      else k_trace_nearest<true, false><<<grid_k1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-    } else {
-      if (pl.trav_stats) k_trace_nearest<false, true><<<grid_k1s_s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-      else k_trace_nearest<false, false><<<grid_k1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-    }
-    launch_shadow(sc, pl, fpp, lv, level, fc, st, pl.trav_stats ? grid_k2_s : grid_k2, launches);
+    launch_trace(sc, level == 0 && !pl.explicit_rays, pl.trav_stats, fpp, lv, level, n_param, fc, st);
+    launch_shadow(sc, pl, fpp, lv, level, fc, st, launches);
     k_shade<<<elem_blocks, 128, 0, st>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc, 0);
     *launches += 2;
   }
@@ -1035,21 +1076,13 @@ int enqueue_frame_async(RtScene *sc, const FramePlan &pl, cudaStream_t st, int *
 int enqueue_level(RtScene *sc, const FramePlan &pl, cudaStream_t cs, int level, cudaGraphConditionalHandle next_cond) {
   const FrameParams *fpp = sc->frame_params.as<FrameParams>();
   FrameCounts *fc = sc->frame_counts.as<FrameCounts>();
-  const DeviceState &G = device_grids();
-  const int g1p = G.g1p, g1s = G.g1s, g2 = G.g2, g1ps = G.g1ps, g1ss = G.g1ss, g2s = G.g2s;
   const int elem_blocks = std::max(1, std::min((pl.n0 + 127) / 128, g_sm_count * 16));
   LevelBufs lv = sc->levels[level].bufs();
   LevelBufs nx = sc->levels[level + 1].bufs();
   const int n_param = level == 0 ? pl.n0 : -1;
   int launches = 0;
-  if (level == 0 && !pl.explicit_rays) {
-    if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
-    else k_trace_nearest<true, false><<<g1p, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
-  } else {
-    if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
-    else k_trace_nearest<false, false><<<g1s, 128, 0, cs>>>(sc->dev, fpp, lv, level, n_param, fc);
-  }
-  launch_shadow(sc, pl, fpp, lv, level, fc, cs, pl.trav_stats ? g2s : g2, &launches);
+  launch_trace(sc, level == 0 && !pl.explicit_rays, pl.trav_stats, fpp, lv, level, n_param, fc, cs);
+  launch_shadow(sc, pl, fpp, lv, level, fc, cs, &launches);
   k_shade<<<elem_blocks, 128, 0, cs>>>(sc->dev, fpp, lv, nx, level, pl.J, pl.Lmax, pl.S, fc, next_cond);
   CUDA_TRY(cudaGetLastError());
   return RT_OK;
@@ -1142,7 +1175,7 @@ struct FusedShape { int J, Lmax, S, depth_cap; bool unbounded; };
 // 0.157 ms as a graph, whose ten dependent launches no longer shrink with the frame.  So the default is "auto":
 // small frames -- the bands of a multi-GPU frame, interactive previews -- and frames of unbounded depth (whose
 // wavefront form needs a host read-back per level) are fused, large single-GPU frames are not.
-bool fused_shape(const FrameParams &fp, long long n_rays, FusedShape *out) {
+bool fused_shape(const FrameParams &fp, long long n_rays, bool plain_scene, FusedShape *out) {
   FusedShape f;
   f.Lmax = std::max(1, fp.n_lights);
   f.S = fp.point_light ? 0 : fp.usteps * fp.vsteps;
@@ -1151,7 +1184,9 @@ bool fused_shape(const FrameParams &fp, long long n_rays, FusedShape *out) {
   f.depth_cap = f.unbounded ? RT_FUSED_MAX_LEVELS - 1 : fp.max_depth;
   if (out) *out = f;
   if (!g_opt_fused || f.J > RT_FUSED_MAX_JOBS || f.depth_cap > RT_FUSED_MAX_LEVELS - 1) return false;
-  if (g_opt_fused == 2 && !f.unbounded && n_rays > 1000LL * g_opt_fused_max_kpix) return false;
+  // (PLAIN scenes -- no spheres, no octree filter, e.g. the bundled cube -- have a much smaller fused kernel, which
+  // beats the wavefront graph at every frame size: 1080p headline frame 0.276 vs 0.301 ms)
+  if (g_opt_fused == 2 && !f.unbounded && !plain_scene && n_rays > 1000LL * g_opt_fused_max_kpix) return false;
   return true;
 }
 
@@ -1166,12 +1201,9 @@ int fused_reserve(RtScene *sc, size_t n0, int depth_cap) {
   return RT_OK;
 }
 
-template <bool STATS>
-int fused_grid() { return STATS ? device_grids().kfs : device_grids().kf; }
-
 int run_fused(RtScene *sc, FrameParams &fp, bool explicit_rays, int n0, cudaStream_t st, bool own_stream, RtStats *stats) {
   FusedShape sh;
-  fused_shape(fp, n0, &sh);
+  fused_shape(fp, n0, scene_is_plain(sc), &sh);
   int rc;
   if ((rc = fused_reserve(sc, (size_t)n0, sh.depth_cap))) return rc;
   FusedBufs fb;
@@ -1187,8 +1219,10 @@ int run_fused(RtScene *sc, FrameParams &fp, bool explicit_rays, int n0, cudaStre
   if (want_stats) cudaEventRecord(ev_a, st);
   int explicit0 = explicit_rays ? 1 : 0, J = sh.J, Lmax = sh.Lmax, S = sh.S, depth_cap = sh.depth_cap, cont_min = g_opt_cont_min;
   void *args[] = {&sc->dev, &fp, &fb, &fc, &n0, &explicit0, &J, &Lmax, &S, &depth_cap, &cont_min};
-  if (trav_stats) CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_frame<true>, dim3(fused_grid<true>()), dim3(128), args, 0, st));
-  else CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_frame<false>, dim3(fused_grid<false>()), dim3(128), args, 0, st));
+  const bool plain = scene_is_plain(sc);
+  const void *kern = trav_stats ? (plain ? (const void *)k_frame<true, true> : (const void *)k_frame<true, false>)
+                                : (plain ? (const void *)k_frame<false, true> : (const void *)k_frame<false, false>);
+  CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(device_grids().g_frame[trav_stats][plain]), dim3(128), args, 0, st));
   if (want_stats) cudaEventRecord(ev_b, st);
   if (want_stats || sh.unbounded) {
     CUDA_TRY(cudaMemcpyAsync(sc->h_fcounts, fc, sizeof(FusedCounts), cudaMemcpyDeviceToHost, st));
@@ -1245,7 +1279,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
   FrameParams fp = fp_in;
   fp.out_rgba = d_rgba; fp.out_face = d_face; fp.out_t = d_t; fp.out_rgbf = d_rgbf;
 
-  if (fused_shape(fp, n0, nullptr)) {
+  if (fused_shape(fp, n0, scene_is_plain(sc), nullptr)) {
     const int frc = run_fused(sc, fp, explicit_rays, n0, st, own_stream, stats);
     if (frc != RT_RETRY_WAVEFRONT) return frc;
   }
@@ -1315,8 +1349,6 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((rc = sc->levels[0].reserve((size_t)n0, (size_t)pl.J))) return rc;
   }
   CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(FrameCounts), st));
-  const DeviceState &G = device_grids();
-  const int g1p = G.g1p, g1s = G.g1s, g2 = G.g2, g1ps = G.g1ps, g1ss = G.g1ss, g2s = G.g2s;
   const int elem_blocks = std::max(1, std::min((n0 + 127) / 128, g_sm_count * 16));
   int levels_run = 0;
   int cur_n = n0;  // host knowledge of the level's ray count (exact in sync mode, upper bound in async mode)
@@ -1324,16 +1356,10 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     LevelBufs lv = sc->levels[level].bufs();
     const int n_param = level == 0 ? n0 : -1;
     timer.begin(0);
-    if (level == 0 && !explicit_rays) {
-      if (pl.trav_stats) k_trace_nearest<true, true><<<g1ps, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-      else k_trace_nearest<true, false><<<g1p, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-    } else {
-      if (pl.trav_stats) k_trace_nearest<false, true><<<g1ss, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-      else k_trace_nearest<false, false><<<g1s, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc);
-    }
+    launch_trace(sc, level == 0 && !explicit_rays, pl.trav_stats, fpp, lv, level, n_param, fc, st);
     timer.end();
     timer.begin(1);
-    launch_shadow(sc, pl, fpp, lv, level, fc, st, pl.trav_stats ? g2s : g2, &launches);
+    launch_shadow(sc, pl, fpp, lv, level, fc, st, &launches);
     timer.end();
     const bool may_spawn = level < pl.depth_cap;
     if (!pl.async) {
@@ -1551,7 +1577,7 @@ extern "C" int rt_trace_rays(RtScene *sc, int64_t n, const float *origins, const
     ho[4 * i + 3] = bits(0); hd[4 * i + 3] = 0.f;
   }
   FusedShape fsh;
-  const bool fused = fused_shape(fp, n, &fsh);
+  const bool fused = fused_shape(fp, n, scene_is_plain(sc), &fsh);
   if (fused) {
     // level-0 slab of the fused frame's ray queue: (o, flags), (d, lp.x), (lp.y, lp.z, parent = none, ray index)
     if ((rc = fused_reserve(sc, (size_t)n, fsh.depth_cap))) return rc;

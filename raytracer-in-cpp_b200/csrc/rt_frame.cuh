@@ -105,7 +105,7 @@ __device__ __forceinline__ V3 fold_chain(const FusedBufs &fb, int parent, V3 c) 
   return c;
 }
 
-template <bool STATS>
+template <bool STATS, bool PLAIN>
 __global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc, const FrameParams fp, const FusedBufs fb,
                                                   FusedCounts *fc, const int n0, const int explicit0, const int J,
                                                   const int Lmax, const int S, const int depth_cap, const int cont_min) {
@@ -183,18 +183,18 @@ __global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc,
         float hit_t = RT_NO_HIT_T;
         int hit_face = -1;
         {
-          Trav<false, STATS> tr;
+          Trav<false, STATS, PLAIN> tr;
           tr.idle();
           bool active = false;
           if (valid) {
             const V3 rdir = recip_dir(d);
             bool tri_enabled = true;
             // raytraceScene's root-box pre-cull on (origin, screen), :576 (skipped with analytic spheres, like rt_oracle.c)
-            if (first) tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || sc.n_spheres > 0;
+            if (first) tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || (!PLAIN && sc.n_spheres > 0);
             // traceRay's own root test on (origin, origin + direction), :655
             const V3 dest = add(o, d);
             tri_enabled = tri_enabled && ref_box_intersect_quick(sc.root_min, sc.root_max, o, dest, recip_dir(sub(dest, o)));
-            if (tri_enabled || sc.n_spheres > 0) {
+            if (tri_enabled || (!PLAIN && sc.n_spheres > 0)) {
               tr.init(o, d, dest, tri_enabled, rdir);
               active = true;
             }
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc,
             }
             const bool want = hit && l < n_l && (s < 0 || any);
             if (!__any_sync(0xffffffffu, want)) continue;
-            Trav<true, STATS> tr;
+            Trav<true, STATS, PLAIN> tr;
             tr.idle();
             bool active = false;
             if (want) {
@@ -244,12 +244,17 @@ __global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc,
                                : (fp.have_sample_table ? ld3(fp.sample_table + 3 * (l * S + s)) : area_sample(fp, ld3(fp.lights + 3 * l), s));
               const V3 sd = sub(P, src);  // :920
               const V3 rdir = recip_dir(sd);
-              const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, P, rdir);  // :924
               traced++;
+              if (STATS) st.box_tests += 1;  // the bounds test
               vis |= 1ull << j;  // visible unless the traversal finds an occluder: t stays FLT_MAX >= 0.98 (:946)
-              if (tri_enabled || sc.n_spheres > 0) {
-                tr.init(src, sd, P, tri_enabled, rdir);
-                active = true;
+              // a segment that cannot reach the BVH's bounds is unoccluded whatever the reference's root-box test
+              // (:924) says: that bit-exact, dearer test is only evaluated for the rays that will be traversed
+              if (segment_reaches_bvh(sc, src, rdir, 0.98f)) {
+                const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, P, rdir);  // :924
+                if (tri_enabled || (!PLAIN && sc.n_spheres > 0)) {
+                  tr.init(src, sd, P, tri_enabled, rdir);
+                  active = true;
+                }
               }
             }
             while (__any_sync(0xffffffffu, active)) {

@@ -98,7 +98,7 @@ __device__ __forceinline__ unsigned long long pool_batch(unsigned long long n_it
   return per_warp >= 96ull ? 96ull : (per_warp >= 64ull ? 64ull : 32ull);
 }
 
-template <bool PRIMARY, bool STATS>
+template <bool PRIMARY, bool STATS, bool PLAIN>
 __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, const FrameParams *__restrict__ fpp,
                                                       const LevelBufs lv, const int level, const int n0,
                                                       FrameCounts *fc) {
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
   const unsigned long long batch = pool_batch(n_items);
   unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of work items (warp-uniform)
 
-  Trav<false, STATS> tr;
+  Trav<false, STATS, PLAIN> tr;
   int stack[RT_STACK_SIZE];
   tr.idle();
 
@@ -166,14 +166,14 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
         if constexpr (PRIMARY) {
           // raytraceScene's root-box pre-cull on (origin, screen), src/flyscene.cpp:576
           // (scenes with analytic spheres -- not a reference feature -- skip it, like rt_oracle.c)
-          tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || sc.n_spheres > 0;
+          tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, o, screen, rdir) || (!PLAIN && sc.n_spheres > 0);
         }
         // traceRay's own root test on (origin, origin+direction), src/flyscene.cpp:655
         // (the reference divides by (o + d) - o, which differs from d by up to ulp(|o|) / |d|: more than the
         // margin of the decisive test for a slow, far-away secondary ray, so that test gets its own reciprocal)
         const V3 dest = add(o, d);
         tri_enabled = tri_enabled && ref_box_intersect_quick(sc.root_min, sc.root_max, o, dest, recip_dir(sub(dest, o)));
-        if (tri_enabled || sc.n_spheres > 0) {  // else: missed the root box, BACKGROUND
+        if (tri_enabled || (!PLAIN && sc.n_spheres > 0)) {  // else: missed the root box, BACKGROUND
           tr.init(o, d, dest, tri_enabled, rdir);
           active = true;
         }
@@ -280,7 +280,7 @@ __device__ __forceinline__ V3 light_sample(const FrameParams &fp, const RayLight
 // all warps of the GPU work on the same one or two samples, which keeps the upper tree levels of that
 // bundle in L1.  j is warp-uniform, the per-job set-up is one 16-byte load of the hit point (hit_p).
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
+template <bool STATS, bool PLAIN>
 __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const FrameParams *__restrict__ fpp,
                                                const LevelBufs lv, const int level, const int J, const int Lmax,
                                                const int S, FrameCounts *fc) {
@@ -290,34 +290,44 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
   unsigned traced = 0;
   const unsigned n_slots = (unsigned)fc->n_hits[level];
   const unsigned n_chunks = (n_slots + 31u) >> 5;
-  const unsigned long long n_units = (unsigned long long)n_chunks * (unsigned long long)J;
-  unsigned long long *cursor = &fc->work_k2[level];
-  const unsigned long long batch = pool_batch(n_units * 32ull) >> 5;  // units per cursor update
-  unsigned long long pool_next = 0, pool_end = 0;                     // warp-local batch of units (warp-uniform)
+  const unsigned n_units = n_chunks * (unsigned)J;  // < 2^27: the host refuses frames with n0 * J >= 2^32
+  // (32-bit cursor in the low word of the 64-bit counter: a warp overshoots n_units by at most one batch)
+  unsigned *cursor = reinterpret_cast<unsigned *>(&fc->work_k2[level]);
+  const unsigned batch = (unsigned)(pool_batch((unsigned long long)n_units * 32ull) >> 5);  // units per cursor update
+  unsigned pool_next = 0, pool_end = 0;  // warp-local batch of units (warp-uniform)
+  // job and chunk of the current unit, advanced incrementally (one division per batch, not per unit)
+  unsigned j = 0, chunk = 0;
+  int l = 0, s = -1;  // light and sample of job j; s < 0: gate ray
 
-  Trav<true, STATS> tr;
+  Trav<true, STATS, PLAIN> tr;
   int stack[RT_STACK_SIZE];
   tr.idle();
 
   for (;;) {
+    bool new_job = false;
     if (pool_next >= pool_end) {
-      unsigned long long base = 0;
+      unsigned base = 0;
       if (lane == 0) base = atomicAdd(cursor, batch);
       base = __shfl_sync(0xffffffffu, base, 0);
       if (base >= n_units) break;
       pool_next = base;
       pool_end = base + batch < n_units ? base + batch : n_units;
+      j = base / n_chunks;
+      chunk = base - j * n_chunks;
+      new_job = true;
+    } else if (++chunk == n_chunks) {
+      chunk = 0; ++j;
+      new_job = true;
     }
-    const unsigned unit = (unsigned)pool_next;
-    pool_next += 1ull;
-    const unsigned j = unit / n_chunks;  // warp-uniform
-    const unsigned slot = (unit - j * n_chunks) * 32u + (unsigned)lane;
-    // light and sample of job j (warp-uniform); s < 0: gate ray
-    int l = (int)j, s = -1;
-    if (j >= (unsigned)Lmax) {
-      const unsigned q = j - (unsigned)Lmax;
-      if (Lmax == 1) { l = 0; s = (int)q; }
-      else { l = (int)(q / (unsigned)S); s = (int)(q - (unsigned)l * (unsigned)S); }
+    pool_next += 1u;
+    const unsigned slot = chunk * 32u + (unsigned)lane;
+    if (new_job) {
+      l = (int)j; s = -1;
+      if (j >= (unsigned)Lmax) {
+        const unsigned q = j - (unsigned)Lmax;
+        if (Lmax == 1) { l = 0; s = (int)q; }
+        else { l = (int)(q / (unsigned)S); s = (int)(q - (unsigned)l * (unsigned)S); }
+      }
     }
     bool active = false, have = false;
     uint8_t visible = 0;
@@ -348,12 +358,17 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
       if (have) {
         const V3 sd = sub(hit, src);  // :920
         const V3 rdir = recip_dir(sd);
-        const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, hit, rdir);  // :924
         traced++;
+        if (STATS) st.box_tests += 1;  // the bounds test
         visible = 1;  // unless the traversal finds an occluder: t stays FLT_MAX >= 0.98 (:946)
-        if (tri_enabled || sc.n_spheres > 0) {
-          tr.init(src, sd, hit, tri_enabled, rdir);
-          active = true;
+        // a segment that cannot reach the BVH's bounds is unoccluded whatever the reference's root-box test (:924)
+        // says, so that (bit-exact, dearer) test is only evaluated for the rays that will be traversed
+        if (segment_reaches_bvh(sc, src, rdir, 0.98f)) {
+          const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, hit, rdir);  // :924
+          if (tri_enabled || (!PLAIN && sc.n_spheres > 0)) {
+            tr.init(src, sd, hit, tri_enabled, rdir);
+            active = true;
+          }
         }
       }
     }

@@ -150,3 +150,24 @@ def test_cpp_facade_members_match_oracle(pkg, oracle_mod, tmp_path):
     assert np.allclose(out["sample24"], (-0.629999995, 1.03499997, 1), atol=1e-8)
     assert out["bb_hit"] == 1 and out["bb_miss"] == 0
     assert out["octree"] == [int(x) for x in orc.octree_stats()]
+
+
+def test_cli_multi_gpu_result_ppm_is_byte_identical(pkg, tmp_path):
+    """`rt_cli --gpus N` (Flyscene::setDevices -> rt_multi_*: the reference's ThreadPool fan-out with GPUs as the
+    workers) writes the same result.ppm, byte for byte, as the single-GPU run."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cli = pkg.build.build_cli()
+    obj = str(tmp_path / "gallery.obj")
+    pkg.scenes.write_gallery(obj, 2)
+    args = ["--scene", obj, "--width", "500", "--height", "301", "--area", "1", "--point", "0", "--max-depth", "3", "--grid", "4", "4"]
+    outs = []
+    for gpus in (1, n):
+        d = tmp_path / f"g{gpus}"
+        d.mkdir()
+        r = subprocess.run([cli] + args + ["--gpus", str(gpus)], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs.append(open(d / "result.ppm", "rb").read())
+    assert outs[0] == outs[1], "multi-GPU result.ppm differs from the single-GPU one"
