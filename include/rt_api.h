@@ -165,6 +165,8 @@ int rt_device_name(char *buf, size_t n);
  *   for scenes without spheres and without an octree filter (<= 1000 triangles, e.g. the bundled cube), for frames of
  *   at most "fused_max_kpixels" thousand rays (default 1200) and for unbounded depth; other frames take the
  *   per-level wavefront kernels of csrc/rt_kernels.cuh -- both paths give bit-identical frames),
+ * "render_chunks" (rt_render of a scene that takes the fused kernel at any size: the frame is rendered in this many row
+ *   chunks, 1..4, default 2, and the device->host copy of a chunk overlaps the rendering of the next),
  * "continue_min_lanes" (fused frame: child rays stay in their warp when at least this many of its lanes spawned one; default 8) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);
@@ -199,6 +201,16 @@ int rt_ref_octree_stats(const RtSceneDesc *desc, int32_t capacity, int64_t out[4
  * reachable once, depth within the traversal stack.  out[6] = nodes, leaves, depth, largest leaf, faces
  * referenced, 1000 x SAH cost.  RT_ERR_INVALID (+ message) names the first violated invariant. */
 int rt_bvh_check(const RtSceneDesc *desc, int32_t leaf_size, int64_t out[6]);
+/* Which builder made the scene's acceleration structures and what came out.  Scenes of at least
+ * "gpu_build_min_prims" primitives (rt_set_option, default 20000; option "gpu_build": 0 never, 1 from 64 primitives on,
+ * 2 = that threshold) are built ON THE DEVICE: the reference octree (BoxTree::BoxTree / split / clasifyFace,
+ * src/boxTree.cpp:11-31, 88-147, 203-336) level by level, the BVH by parallel locally-ordered clustering over a Morton
+ * order, the primitive soup and the shading table by one thread per primitive (csrc/rt_build.cuh).  out[16] =
+ * built on the GPU (0/1), BVH pair nodes, leaves, depth, 1000 x SAH cost (the definition of rt_bvh_check),
+ * octree leaves / inner nodes / face references / largest leaf (the numbers of rt_ref_octree_stats),
+ * build microseconds: total, input upload, octree, Morton sort, clustering, emit + bake; 1000 x octree levels +
+ * clustering rounds. */
+int rt_scene_build_info(const RtScene *scene, int64_t out[16]);
 /* debug / test access to the flattened BVH (host copies): nodes [n_nodes][16] floats as uploaded,
  * tri_face [n_tris] original face id of each soup slot */
 int rt_scene_debug_bvh(const RtScene *scene, float *nodes, int64_t nodes_cap, int32_t *tri_face, int64_t tri_cap);

@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"]
 
 LIB_SOURCES = ["csrc/rt_api.cu", "host/obj_loader.cpp", "host/bvh_builder.cpp", "host/ref_octree.cpp"]
-LIB_DEPS = LIB_SOURCES + ["csrc/rt_device.cuh", "csrc/rt_kernels.cuh", "csrc/rt_frame.cuh", "csrc/rt_multi.inl", "host/obj_loader.hpp", "host/bvh_builder.hpp",
+LIB_DEPS = LIB_SOURCES + ["csrc/rt_device.cuh", "csrc/rt_kernels.cuh", "csrc/rt_frame.cuh", "csrc/rt_multi.inl", "csrc/rt_build.cuh", "csrc/rt_gpu_build.inl", "host/obj_loader.hpp", "host/bvh_builder.hpp",
                           "host/vec3.hpp", "host/ref_octree.hpp", "../include/rt_api.h"]
 CLI_SOURCES = ["host/rt_cli.cpp", "host/flyscene.cpp"]
 CLI_DEPS = CLI_SOURCES + ["host/flyscene.hpp", "host/vec3.hpp", "../include/rt_api.h"]

@@ -72,7 +72,7 @@ API_SYMBOLS = [
     "rt_api_version", "rt_init", "rt_shutdown", "rt_last_error", "rt_device_name", "rt_set_option",
     "rt_default_params", "rt_mesh_load_obj", "rt_mesh_desc", "rt_mesh_info", "rt_mesh_destroy",
     "rt_scene_create", "rt_scene_destroy", "rt_scene_root_box", "rt_scene_info", "rt_ref_octree_stats",
-    "rt_scene_debug_bvh", "rt_bvh_check",
+    "rt_scene_debug_bvh", "rt_bvh_check", "rt_scene_build_info",
     "rt_render", "rt_render_device", "rt_render_submit", "rt_render_wait", "rt_local_rows", "rt_local_row_map", "rt_shared_frame_create",
     "rt_shared_frame_open", "rt_shared_frame_close", "rt_device_copy_to_host", "rt_trace_rays",
     "rt_light_strikes", "rt_box_intersect", "rt_box_intersect_box", "rt_ray_triangle", "rt_octree_candidates",
@@ -111,6 +111,7 @@ def lib():
     L.rt_scene_destroy.restype = None
     L.rt_scene_root_box.argtypes = [vp, vp, vp]
     L.rt_scene_info.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rt_scene_build_info.argtypes = [vp, vp]
     L.rt_scene_debug_bvh.argtypes = [vp, vp, i64, vp, i64]
     L.rt_ref_octree_stats.argtypes = [C.POINTER(RtSceneDesc), i32, vp]
     L.rt_bvh_check.argtypes = [C.POINTER(RtSceneDesc), i32, vp]
@@ -353,6 +354,15 @@ class Scene:
         ms = C.c_float()
         _check(lib().rt_scene_info(self.h, *[C.byref(x) for x in v], C.byref(ms)))
         return dict(nodes=v[0].value, leaves=v[1].value, prims=v[2].value, device_bytes=v[3].value, build_ms=ms.value)
+
+    def build_info(self):
+        """rt_scene_build_info: which builder made the acceleration structures and what came out."""
+        o = np.zeros(16, np.int64)
+        _check(lib().rt_scene_build_info(self.h, _ptr(o)))
+        return dict(gpu=bool(o[0]), nodes=int(o[1]), leaves=int(o[2]), depth=int(o[3]), sah=o[4] / 1000.0,
+                    octree=dict(leaves=int(o[5]), inner=int(o[6]), refs=int(o[7]), max_leaf=int(o[8])),
+                    build_ms=o[9] / 1000.0, upload_ms=o[10] / 1000.0, octree_ms=o[11] / 1000.0, sort_ms=o[12] / 1000.0,
+                    cluster_ms=o[13] / 1000.0, emit_ms=o[14] / 1000.0, octree_levels=int(o[15] // 1000), cluster_rounds=int(o[15] % 1000))
 
     def debug_bvh(self):
         inf = self.info()

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -25,6 +26,7 @@
 #include "../host/ref_octree.hpp"
 #include "rt_kernels.cuh"
 #include "rt_frame.cuh"
+#include "rt_build.cuh"
 
 using namespace rtd;
 
@@ -44,7 +46,7 @@ struct DeviceState {
   int sm_count = 0;
   int grids_opt = -1;  // value of persistent_ctas_per_sm the grids below were computed for
   // persistent grid sizes: [primary rays?][stats build?][plain scene?]
-  int g_trace[2][2][2] = {}, g_shadow[2][2] = {}, g_frame[2][2] = {};
+  int g_trace[2][2][2] = {}, g_shadow[2][2] = {}, g_frame[2][2] = {}, g_shadow_stream[2] = {};
 };
 constexpr int kMaxDevices = 64;
 DeviceState g_devs[kMaxDevices];
@@ -57,6 +59,14 @@ int g_opt_fused = 2;       // frame as ONE persistent kernel (rt_frame.cuh): 0 n
                            // 1 whenever the frame is eligible, 2 (default) when it is also small enough (below)
 int g_opt_fused_max_kpix = 1200;  // auto mode: frames of at most this many thousand rays take the fused kernel
 int g_opt_cont_min = 8;    // fused frame: child rays stay in the warp when at least this many lanes spawned one
+int g_opt_gpu_build = 2;   // acceleration structures built on the device (rt_gpu_build.inl): 0 never, 1 whenever the scene has
+                           // at least 64 primitives, 2 (default) from gpu_build_min_prims primitives on
+int g_opt_gpu_build_min = 20000;
+int g_opt_chunks = 2;      // rt_render: row chunks whose device->host copy overlaps the rendering of the next chunk
+int g_opt_shadow_stream = 0;    // K2 with lane-level ray replacement (k_shadow_stream) on scenes with an octree filter / spheres
+int g_opt_refill_min = 8;       //   lanes that must be free before new rays are handed out
+int g_opt_leaf_quorum = 16;     //   lanes holding a postponed leaf that end the node phase
+int g_opt_stream_rays = 256;    //   rays a warp takes per cursor update
 
 int fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -169,6 +179,11 @@ struct RtScene {
   int64_t n_leaves = 0;
   float build_ms = 0.f;
   int bvh_depth = 0;
+  double sah_cost = 0.0;            // bvh_builder.cpp's definition, for either builder
+  bool built_on_gpu = false;        // rt_gpu_build.inl
+  DevBuf prim_order;                // GPU build: soup slot -> primitive id (host copy fetched on demand)
+  float build_phase_ms[5] = {0, 0, 0, 0, 0};  // GPU build: upload, octree, sort, clustering, emit + bake
+  int build_rounds[2] = {0, 0};     // GPU build: octree levels, clustering rounds
   // per-frame workspace
   std::vector<LevelStore> levels;
   DevBuf frame_counts;    // FrameCounts
@@ -180,6 +195,7 @@ struct RtScene {
   cudaStream_t copy_stream = nullptr;
   DevBuf slot_rgba[2];
   cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};  // rt_render: chunk c rendered
   bool slot_busy[2] = {false, false};
   int submit_seq = 0;
   // fused frame kernel (rt_frame.cuh): deferred-ray slabs, chain records, counters
@@ -291,6 +307,13 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "graph_conditionals")) g_opt_graph_cond = value ? 1 : 0;
   else if (!strcmp(key, "fused_frame")) g_opt_fused = std::max(0, std::min(2, value));
   else if (!strcmp(key, "fused_max_kpixels")) g_opt_fused_max_kpix = std::max(0, value);
+  else if (!strcmp(key, "gpu_build")) g_opt_gpu_build = std::max(0, std::min(2, value));
+  else if (!strcmp(key, "gpu_build_min_prims")) g_opt_gpu_build_min = std::max(64, value);
+  else if (!strcmp(key, "render_chunks")) g_opt_chunks = std::max(1, std::min(4, value));
+  else if (!strcmp(key, "shadow_stream")) g_opt_shadow_stream = value ? 1 : 0;
+  else if (!strcmp(key, "refill_min_lanes")) g_opt_refill_min = std::max(1, std::min(32, value));
+  else if (!strcmp(key, "leaf_quorum")) g_opt_leaf_quorum = std::max(1, std::min(33, value));
+  else if (!strcmp(key, "stream_rays")) g_opt_stream_rays = std::max(32, std::min(1 << 16, value)) & ~31;
   else if (!strcmp(key, "continue_min_lanes")) g_opt_cont_min = std::max(1, std::min(33, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
@@ -380,6 +403,7 @@ struct HostBake {
   bool use_filter = false;
   int64_t n_leaves = 0, oct_stats[4] = {0, 0, 0, 0};
   int bvh_depth = 0;
+  double sah_cost = 0.0;
   float octree_ms = 0.f, bake_ms = 0.f;
 };
 
@@ -499,6 +523,7 @@ void bake_scene(const RtSceneDesc *desc, HostBake &hb) {
   rt::BvhBuildResult bvh = rt::build_bvh(boxes, kind, g_opt_leaf, pad, threads);
   hb.n_leaves = bvh.n_leaves;
   hb.bvh_depth = bvh.max_depth;
+  hb.sah_cost = bvh.sah_cost;
 
   // ---- primitive soup in leaf order (80 B / primitive) ----
   std::vector<float> &prims = hb.prims;
@@ -603,6 +628,7 @@ int upload_scene(const HostBake &hb, RtScene **out) {
   sc->h_prim_face = hb.prim_face;
   sc->n_leaves = hb.n_leaves;
   sc->bvh_depth = hb.bvh_depth;
+  sc->sah_cost = hb.sah_cost;
   sc->octree_ms = hb.octree_ms;
   memcpy(sc->oct_stats, hb.oct_stats, sizeof(hb.oct_stats));
   int rc;
@@ -647,11 +673,26 @@ int upload_scene(const HostBake &hb, RtScene **out) {
 
 }  // namespace
 
+#include "rt_gpu_build.inl"
+
+namespace {
+bool wants_gpu_build(const RtSceneDesc *desc) {
+  const long long n = (long long)desc->n_faces + desc->n_spheres;
+  return g_opt_gpu_build != 0 && n >= (g_opt_gpu_build == 1 ? 64 : (long long)g_opt_gpu_build_min);
+}
+}  // namespace
+
 extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
   if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
   int rc = validate_scene_desc(desc);
   if (rc) return rc;
   if ((rc = ensure_device())) return rc;
+  if (wants_gpu_build(desc)) {
+    bool too_deep = false;
+    if ((rc = gpu_build_scene(desc, out, &too_deep))) return rc;
+    if (!too_deep) return RT_OK;
+    // (a clustered tree deeper than the traversal stack: the host builder bounds its depth by construction)
+  }
   HostBake hb;
   bake_scene(desc, hb);
   return upload_scene(hb, out);
@@ -681,7 +722,7 @@ extern "C" void rt_scene_destroy(RtScene *sc) {
   use_device(sc->device);
   sc->nodes.release(); sc->prims.release(); sc->shade.release(); sc->mats.release();
   sc->spheres.release(); sc->sphere_mat.release();
-  sc->oct_box.release(); sc->oct_face_off.release(); sc->oct_face_leaf.release();
+  sc->oct_box.release(); sc->oct_face_off.release(); sc->oct_face_leaf.release(); sc->prim_order.release();
   for (auto &l : sc->levels) l.release();
   sc->frame_counts.release(); sc->frame_params.release();
   if (sc->graph_exec) cudaGraphExecDestroy(sc->graph_exec);
@@ -692,6 +733,8 @@ extern "C" void rt_scene_destroy(RtScene *sc) {
     if (sc->ev_copied[k]) cudaEventDestroy(sc->ev_copied[k]);
     sc->slot_rgba[k].release();
   }
+  for (int k = 0; k < 4; ++k)
+    if (sc->ev_chunk[k]) cudaEventDestroy(sc->ev_chunk[k]);
   sc->out_rgba.release(); sc->out_face.release(); sc->out_t.release(); sc->out_rgbf.release();
   sc->in_a.release(); sc->in_b.release();
   if (sc->h_counts) cudaFreeHost(sc->h_counts);
@@ -810,8 +853,31 @@ extern "C" int rt_bvh_check(const RtSceneDesc *desc, int32_t leaf_size, int64_t 
   return RT_OK;
 }
 
-extern "C" int rt_scene_debug_bvh(const RtScene *sc, float *nodes, int64_t nodes_cap, int32_t *tri_face, int64_t tri_cap) {
-  if (!sc) return fail(RT_ERR_INVALID, "null scene");
+// Which builder made the scene's acceleration structures, and what came out.
+extern "C" int rt_scene_build_info(const RtScene *sc, int64_t out[16]) {
+  if (!sc || !out) return fail(RT_ERR_INVALID, "null argument");
+  out[0] = sc->built_on_gpu ? 1 : 0;
+  out[1] = sc->dev.n_nodes; out[2] = sc->n_leaves; out[3] = sc->bvh_depth;
+  out[4] = (int64_t)(sc->sah_cost * 1000.0);
+  for (int k = 0; k < 4; ++k) out[5 + k] = sc->oct_stats[k];
+  out[9] = (int64_t)(sc->build_ms * 1000.f);
+  for (int k = 0; k < 5; ++k) out[10 + k] = (int64_t)(sc->build_phase_ms[k] * 1000.f);
+  out[15] = (int64_t)sc->build_rounds[0] * 1000 + sc->build_rounds[1];
+  return RT_OK;
+}
+
+extern "C" int rt_scene_debug_bvh(const RtScene *sc_in, float *nodes, int64_t nodes_cap, int32_t *tri_face, int64_t tri_cap) {
+  if (!sc_in) return fail(RT_ERR_INVALID, "null scene");
+  RtScene *sc = const_cast<RtScene *>(sc_in);
+  if (sc->built_on_gpu && sc->h_nodes.empty() && sc->dev.n_nodes > 0) {
+    // scenes built on the device keep no host copy: fetch one on first use
+    int rc = use_device(sc->device);
+    if (rc) return rc;
+    sc->h_nodes.resize((size_t)sc->dev.n_nodes);
+    sc->h_prim_face.resize((size_t)sc->dev.n_prims);
+    CUDA_TRY(cudaMemcpy(sc->h_nodes.data(), sc->nodes.p, sc->h_nodes.size() * sizeof(rt::PairNode), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(sc->h_prim_face.data(), sc->prim_order.p, sc->h_prim_face.size() * 4, cudaMemcpyDeviceToHost));
+  }
   if (nodes) {
     if (nodes_cap < (int64_t)sc->h_nodes.size()) return fail(RT_ERR_INVALID, "nodes buffer too small");
     memcpy(nodes, sc->h_nodes.data(), sc->h_nodes.size() * sizeof(rt::PairNode));
@@ -985,6 +1051,7 @@ const DeviceState &device_grids() {
     d.g_trace[1][1][1] = persistent_grid(k_trace_nearest<true, true, true>, 128);
     d.g_shadow[0][0] = persistent_grid(k_shadow<false, false>, 128); d.g_shadow[0][1] = persistent_grid(k_shadow<false, true>, 128);
     d.g_shadow[1][0] = persistent_grid(k_shadow<true, false>, 128); d.g_shadow[1][1] = persistent_grid(k_shadow<true, true>, 128);
+    d.g_shadow_stream[0] = persistent_grid(k_shadow_stream<false>, 128); d.g_shadow_stream[1] = persistent_grid(k_shadow_stream<true>, 128);
     d.g_frame[0][0] = persistent_grid(k_frame<false, false>, 128); d.g_frame[0][1] = persistent_grid(k_frame<false, true>, 128);
     d.g_frame[1][0] = persistent_grid(k_frame<true, false>, 128); d.g_frame[1][1] = persistent_grid(k_frame<true, true>, 128);
     d.grids_opt = g_opt_ctas_per_sm;
@@ -1032,6 +1099,15 @@ void launch_trace(RtScene *sc, bool primary, bool stats, const FrameParams *fpp,
 void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, const LevelBufs &lv, int level, FrameCounts *fc,
                    cudaStream_t st, int *launches) {
   const bool plain = scene_is_plain(sc);
+  if (!plain && g_opt_shadow_stream) {
+    const int g = device_grids().g_shadow_stream[pl.trav_stats];
+    if (pl.trav_stats)
+      k_shadow_stream<true><<<g, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, g_opt_refill_min, g_opt_leaf_quorum, (unsigned)g_opt_stream_rays);
+    else
+      k_shadow_stream<false><<<g, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, g_opt_refill_min, g_opt_leaf_quorum, (unsigned)g_opt_stream_rays);
+    *launches += 1;
+    return;
+  }
   const int grid = device_grids().g_shadow[pl.trav_stats][plain];
 #define RT_K2(STATS_, PLAIN_) k_shadow<STATS_, PLAIN_><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc)
   if (pl.trav_stats) { if (plain) RT_K2(true, true); else RT_K2(true, false); }
@@ -1313,7 +1389,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
     for (int l = 0; l <= pl.depth_cap; ++l)
       if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
-    const std::vector<long long> key = {g_alloc_generation.load(), n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, g_opt_graph_cond, g_opt_ctas_per_sm,
+    const std::vector<long long> key = {g_alloc_generation.load(), n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, g_opt_graph_cond, g_opt_ctas_per_sm, g_opt_shadow_stream, g_opt_refill_min, g_opt_leaf_quorum, g_opt_stream_rays,
                                         (long long)pl.explicit_rays, (long long)pl.trav_stats};
     if (sc->graph_exec == nullptr || key != sc->graph_key) {
       if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }
@@ -1457,6 +1533,35 @@ extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *light
   p = &local_p;
   // everything on the scene's own stream: frame, copies, one synchronisation at the end
   cudaStream_t st = sc->stream;
+  // Only the packed frame is wanted, the whole image is rendered by this call and the scene takes the fused kernel
+  // at any size: render it in row chunks (one launch each) and copy chunk c to the host while chunk c+1 is being
+  // rendered -- the 8.3 MB of a 1080p frame otherwise add 0.17 ms of PCIe time behind a 0.28 ms frame.
+  if (g_opt_chunks > 1 && !face_out && !t_out && !rgb_f32_out && !stats && cam && lights && p->band_world <= 1 &&
+      p->height >= 64 * g_opt_chunks && p->width > 0 && scene_is_plain(sc)) {
+    const int C = g_opt_chunks, H = p->height, W = p->width;
+    const int B = (((H + C - 1) / C) + 3) & ~3;  // rows per chunk, a multiple of the 8x4 tile height
+    FrameParams probe;
+    if ((rc = fill_frame(probe, cam, lights, p))) return rc;
+    if (fused_shape(probe, (long long)B * W, true, nullptr)) {
+      if (!sc->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
+      for (int c = 0; c < C; ++c)
+        if (!sc->ev_chunk[c]) CUDA_TRY(cudaEventCreateWithFlags(&sc->ev_chunk[c], cudaEventDisableTiming));
+      for (int c = 0; c < C; ++c) {
+        RtParams cp = *p;
+        cp.band_rows = B; cp.band_rank = c; cp.band_world = C; cp.out_full_frame = 1;
+        const int rows = rt_local_rows(&cp);
+        if (rows <= 0) continue;
+        if ((rc = rt_render_device(sc, cam, lights, &cp, sc->out_rgba.p, nullptr, nullptr, nullptr, st, nullptr))) return rc;
+        CUDA_TRY(cudaEventRecord(sc->ev_chunk[c], st));
+        CUDA_TRY(cudaStreamWaitEvent(sc->copy_stream, sc->ev_chunk[c], 0));
+        const size_t off = (size_t)c * (size_t)B * (size_t)W * 4;
+        CUDA_TRY(cudaMemcpyAsync(rgba_out + off, (const uint8_t *)sc->out_rgba.p + off, (size_t)rows * (size_t)W * 4,
+                                 cudaMemcpyDeviceToHost, sc->copy_stream));
+      }
+      CUDA_TRY(cudaStreamSynchronize(sc->copy_stream));
+      return RT_OK;
+    }
+  }
   rc = rt_render_device(sc, cam, lights, p, sc->out_rgba.p, face_out ? sc->out_face.as<int32_t>() : nullptr,
                         t_out ? sc->out_t.as<float>() : nullptr, rgb_f32_out ? sc->out_rgbf.as<float>() : nullptr,
                         st, stats);

@@ -404,6 +404,133 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
 
 
 // ---------------------------------------------------------------------------------------------
+// K2, streaming form for traversal-heavy scenes: the same jobs in the same order, but a warp does not wait for the
+// longest of its 32 rays before it takes the next 32.  Any-hit rays of one tile end after very different numbers of
+// steps (profiles/r01_c3_ncu_final.txt: 11 of 32 lanes active in the node loop of k_shadow on the 1 M-triangle
+// frame), so every warp owns a run of consecutive rays (job-major order, `stream_rays` of them per cursor update)
+// and hands the next ray of that run to a lane as soon as at least `refill_min` lanes have finished theirs.
+// A ray is identified by R = unit * 32 + lane-in-unit (unit = job * n_chunks + chunk, as in k_shadow).
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(128, 7) k_shadow_stream(const DevScene sc, const FrameParams *__restrict__ fpp,
+                                                      const LevelBufs lv, const int level, const int J, const int Lmax,
+                                                      const int S, FrameCounts *fc, const int refill_min,
+                                                      const int leaf_quorum, const unsigned stream_rays) {
+  RT_STAGE_FRAME_PARAMS(fpp);
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
+  unsigned traced = 0;
+  const unsigned n_slots = (unsigned)fc->n_hits[level];
+  const unsigned n_chunks = (n_slots + 31u) >> 5;
+  const unsigned n_rays = n_chunks * (unsigned)J * 32u;  // < 2^32 (checked by the host)
+  unsigned *cursor = reinterpret_cast<unsigned *>(&fc->work_k2[level]);
+  unsigned r_next = 0, r_end = 0;  // the warp's run of rays (warp-uniform)
+  bool exhausted = n_rays == 0u;
+
+  Trav<true, STATS, false> tr;
+  int stack[RT_STACK_SIZE];
+  tr.idle();
+  bool active = false;
+  unsigned my_slot = 0, my_j = 0;
+
+  for (;;) {
+    // ---- hand rays to the lanes that have none ----
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    const int n_idle = __popc(idle);
+    if (!exhausted && (n_idle >= refill_min || n_idle == 32)) {
+      if (r_next >= r_end) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(cursor, stream_rays);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_rays) exhausted = true;
+        else { r_next = base; r_end = base + stream_rays < n_rays ? base + stream_rays : n_rays; }
+      }
+      if (!exhausted) {
+        const unsigned R = r_next + (unsigned)__popc(idle & lt_mask);
+        const bool take = !active && R < r_end;
+        const unsigned left = r_end - r_next;
+        r_next += (unsigned)n_idle < left ? (unsigned)n_idle : left;
+        if (take) {
+          const unsigned unit = R >> 5;
+          const unsigned j = unit / n_chunks;
+          const unsigned slot = (unit - j * n_chunks) * 32u + (R & 31u);
+          int l = (int)j, s = -1;
+          if (j >= (unsigned)Lmax) {
+            const unsigned q = j - (unsigned)Lmax;
+            if (Lmax == 1) { l = 0; s = (int)q; }
+            else { l = (int)(q / (unsigned)S); s = (int)(q - (unsigned)l * (unsigned)S); }
+          }
+          if (slot < n_slots) {
+            const float2 hxy = *reinterpret_cast<const float2 *>(lv.hit_p + slot);
+            const V3 hit = mk(hxy.x, hxy.y, reinterpret_cast<const float *>(lv.hit_p + slot)[2]);
+            const int iw = *reinterpret_cast<volatile const int *>(reinterpret_cast<const int *>(lv.hit_p + slot) + 3);
+            V3 src;
+            bool have;
+            if (iw & 1) {
+              have = l == 0;
+              const int i = (iw & ~RT_HIT_DARK) >> 1;
+              const V3 lp = mk(lv.ray_d[i].w, lv.ray_l[i].x, lv.ray_l[i].y);
+              src = s < 0 ? lp : area_sample(fp, lp, s);
+            } else {
+              have = l < fp.n_lights;
+              src = s < 0 ? ld3(fp.lights + 3 * l)
+                          : (fp.have_sample_table ? ld3(fp.sample_table + 3 * (l * S + s)) : area_sample(fp, ld3(fp.lights + 3 * l), s));
+            }
+            if (s >= 0 && (iw & RT_HIT_DARK)) have = false;  // see k_shadow
+            uint8_t visible = 0;
+            if (have) {
+              const V3 sd = sub(hit, src);
+              const V3 rdir = recip_dir(sd);
+              traced++;
+              if (STATS) st.box_tests += 1;
+              visible = 1;
+              if (segment_reaches_bvh(sc, src, rdir, 0.98f)) {
+                const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, hit, rdir);
+                if (tri_enabled || sc.n_spheres > 0) {
+                  tr.init(src, sd, hit, tri_enabled, rdir);
+                  active = true;
+                  my_slot = slot; my_j = j;
+                }
+              }
+            }
+            if (!active) lv.vis[(size_t)slot * (size_t)J + j] = visible;  // decided without a traversal (never a dark gate)
+          }
+        }
+        continue;  // lanes that got a ray needing no traversal are idle again: look once more
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- traverse until enough lanes are free again (to the end once no ray is left to hand out) ----
+    tr.run_stream(sc, st, stack, exhausted ? 32 : refill_min, leaf_quorum);
+    // ---- retire the finished rays ----
+    if (active && tr.traversal_done() && tr.finish(sc, st)) {
+      active = false;
+      const uint8_t visible = tr.occluded ? 0 : 1;
+      lv.vis[(size_t)my_slot * (size_t)J + my_j] = visible;
+      if (my_j == 0u && S > 0 && visible == 0) {
+        int *w = reinterpret_cast<int *>(lv.hit_p + my_slot) + 3;
+        const int iw = *reinterpret_cast<volatile int *>(w);
+        if ((iw & 1) || fp.n_lights == 1) atomicOr(w, RT_HIT_DARK);
+      }
+      tr.idle();
+    }
+  }
+  if (STATS) {
+    warp_sum_add(&fc->ctr.shadow_rays_traced, traced);
+    warp_sum_add(&fc->ctr.box_tests_k2, st.box_tests);
+    warp_sum_add(&fc->ctr.tri_tests_k2, st.tri_tests);
+    warp_sum_add(&fc->ctr.filter_checks, st.filter_checks);
+    warp_sum_add(&fc->ctr.filter_slow, st.filter_slow);
+    warp_sum_add(&fc->ctr.filter_rejects, st.filter_rejects);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // shading helpers
 // ---------------------------------------------------------------------------------------------
 struct Material {

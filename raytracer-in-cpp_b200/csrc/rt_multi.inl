@@ -198,8 +198,11 @@ extern "C" int rt_multi_create(const RtSceneDesc *desc, int n_devices, const int
       if (std::find(uniq.begin(), uniq.end(), devices[k]) == uniq.end()) uniq.push_back(devices[k]);
     if ((rc = rt_init_devices((int)uniq.size(), uniq.data()))) return rc;
   }
+  // Large scenes are built on every device by the device itself (rt_gpu_build.inl); otherwise the host work (BVH,
+  // octree filter, soup) is done once for all devices.
+  bool gpu_build = wants_gpu_build(desc);
   HostBake hb;
-  bake_scene(desc, hb);  // the host work (BVH, octree filter, soup) is done once for all devices
+  if (!gpu_build) bake_scene(desc, hb);
   RtMulti *m = new RtMulti();
   m->n = n_devices;
   m->devices.assign(devices, devices + n_devices);
@@ -209,7 +212,13 @@ extern "C" int rt_multi_create(const RtSceneDesc *desc, int n_devices, const int
   m->ms.assign((size_t)n_devices, 0.f);
   for (int k = 0; k < n_devices; ++k) {
     RtScene *sc = nullptr;
-    if ((rc = use_device(devices[k])) || (rc = upload_scene(hb, &sc))) { rt_multi_destroy(m); return rc; }
+    if ((rc = use_device(devices[k]))) { rt_multi_destroy(m); return rc; }
+    if (gpu_build) {
+      bool too_deep = false;
+      if ((rc = gpu_build_scene(desc, &sc, &too_deep))) { rt_multi_destroy(m); return rc; }
+      if (too_deep) { gpu_build = false; bake_scene(desc, hb); }
+    }
+    if (!gpu_build && (rc = upload_scene(hb, &sc))) { rt_multi_destroy(m); return rc; }
     m->scenes.push_back(sc);
     cudaEvent_t a = nullptr, b = nullptr;
     cudaEventCreate(&a); cudaEventCreate(&b);

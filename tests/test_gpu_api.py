@@ -510,3 +510,29 @@ def test_shutdown_releases_workspaces_and_scenes_stay_usable(pkg):
     b = scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False).rgba
     assert (a == b).all()
     scene.close()
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 4])
+def test_chunked_render_equals_single_launch(chunks, pkg):
+    """rt_render of a plain scene (the bundled cube) renders the frame in row chunks so that the device->host copy of
+    one chunk overlaps the rendering of the next ("render_chunks"): same frame, byte for byte, for chunk heights
+    that are not multiples of the image height, for tiny images (no chunking) and for every depth mode."""
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden("cube_point_1000")
+    scene = capi.Scene(g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    try:
+        for (W, H, area, point, depth) in [(640, 363, 1, 0, 3), (501, 1001, 0, 1, -1), (320, 130, 1, 0, 3), (1920, 1080, 1, 0, 3)]:
+            cam = capi.default_camera(W, H)
+            params = capi.make_params(W, H, area, point, depth, (4, 4))
+            capi.set_option("render_chunks", 1)
+            ref = scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False).rgba
+            capi.set_option("render_chunks", chunks)
+            got = scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False).rgba
+            assert (got == ref).all(), (W, H, chunks)
+            full = scene.render(cam, lights, params)   # with face / t / float outputs: the unchunked path
+            assert (full.rgba == ref).all()
+    finally:
+        capi.set_option("render_chunks", 2)
+    scene.close()

@@ -1,0 +1,145 @@
+"""The acceleration structures built ON the GPU (csrc/rt_build.cuh, rt_gpu_build.inl) against the host builders:
+the reference octree must be the same octree (shape and candidate sets), the BVH must satisfy what the traversal
+relies on, and every frame must be the frame of the host-built scene, bit for bit."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import case_params, load_golden, scene_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+def build_both(capi, arrays, model=None, spheres=None, sphere_mat=None):
+    capi.init(0)
+    try:
+        capi.set_option("gpu_build", 0)
+        host = capi.Scene(*arrays, model, spheres, sphere_mat)
+        capi.set_option("gpu_build", 1)
+        dev = capi.Scene(*arrays, model, spheres, sphere_mat)
+    finally:
+        capi.set_option("gpu_build", 2)
+    assert not host.build_info()["gpu"] and dev.build_info()["gpu"]
+    return host, dev
+
+
+def check_tree(nodes, tri, boxes_min, boxes_max, n_prims):
+    """Every primitive in exactly one leaf, every leaf box containing its primitives, every child box inside its
+    parent's, every node reached once, depth within the traversal stack."""
+    code = nodes[:, 12:14].copy().view(np.int32)
+    seen_node = np.zeros(len(nodes), np.int32)
+    seen_slot = np.zeros(n_prims, np.int32)
+    inf = np.float32(np.inf)
+    todo = [(0, 1, np.full(3, -inf), np.full(3, inf))]
+    max_depth = 0
+    while todo:
+        n, depth, pmn, pmx = todo.pop()
+        seen_node[n] += 1
+        max_depth = max(max_depth, depth)
+        q = nodes[n]
+        for c in range(2):
+            mn = np.array([q[4 * c + 0], q[4 * c + 2], q[8 + 2 * c]])
+            mx = np.array([q[4 * c + 1], q[4 * c + 3], q[9 + 2 * c]])
+            assert (mn <= mx).all() and (mn >= pmn).all() and (mx <= pmx).all(), f"node {n} child {c}: box not inside its parent's"
+            cd = int(code[n, c])
+            if cd >= 0:
+                todo.append((cd, depth + 1, mn, mx))
+                continue
+            lc = (~cd) & 0xffffffff
+            first, count = lc >> 5, (lc & 15) + 1
+            assert first + count <= n_prims
+            seen_slot[first:first + count] += 1
+            p = tri[first:first + count]
+            assert (boxes_min[p] >= mn).all() and (boxes_max[p] <= mx).all(), f"leaf of node {n}: a primitive sticks out"
+    assert (seen_node == 1).all() and (seen_slot == 1).all()
+    assert np.array_equal(np.sort(tri), np.arange(n_prims))
+    assert max_depth <= 60
+    return max_depth
+
+
+@pytest.mark.parametrize("case", ["hf32_point_256x144", "gallery_area_200x150", "dodge_point_1000", "hf224_point_3840x2160_s24"])
+def test_gpu_built_scene_equals_host_built_scene(case, pkg, capi, scene_dir):
+    g = load_golden(case)
+    arrays = scene_arrays(case, pkg, scene_dir)
+    host, dev = build_both(capi, arrays, g["model_matrix"])
+    hi, di = host.build_info(), dev.build_info()
+    print(case, "host", hi, "\n gpu", di)
+    # the reference octree: same shape ...
+    assert di["octree"] == hi["octree"]
+    if "octree_stats" in g.z.files:  # the numbers of the reference's own BoxTree for this scene
+        assert [int(x) for x in g["octree_stats"]] == [di["octree"][k] for k in ("leaves", "inner", "refs", "max_leaf")]
+    # ... and the same candidate sets for rays through the scene
+    mn, mx = host.root_box()
+    dmn, dmx = dev.root_box()
+    assert (mn.view(np.uint32) == dmn.view(np.uint32)).all() and (mx.view(np.uint32) == dmx.view(np.uint32)).all()
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        o = (mn + (mx - mn) * rng.uniform(-0.5, 1.5, 3)).astype(np.float32)
+        d = (mn + (mx - mn) * rng.uniform(0.0, 1.0, 3)).astype(np.float32)
+        a, b = host.octree_candidates(o, d), dev.octree_candidates(o, d)
+        assert np.array_equal(np.sort(a), np.sort(b))
+    # the BVH: invariants of the traversal, quality comparable to the binned-SAH host tree
+    verts = arrays[0].reshape(-1, 3, 3)
+    nodes, tri = dev.debug_bvh()
+    depth = check_tree(nodes, tri, verts.min(1), verts.max(1), len(verts))
+    assert di["nodes"] == len(nodes) and depth <= di["depth"] + 1
+    assert di["sah"] <= 1.25 * hi["sah"], (di["sah"], hi["sah"])
+    # the frame: bit for bit
+    cp = case_params(g)
+    cam = capi.make_camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    lights = capi.Lights(g["lights"], g["light_color"])
+    W, H = (cp["w"], cp["h"]) if cp["w"] * cp["h"] <= 1 << 20 else (cp["w"] // 4, cp["h"] // 4)
+    if (W, H) != (cp["w"], cp["h"]):
+        cam = capi.default_camera(W, H)
+    params = capi.make_params(W, H, cp["area"], cp["point"], cp["max_depth"], cp["grid"])
+    a, b = host.render(cam, lights, params), dev.render(cam, lights, params)
+    assert (a.face == b.face).all() and (a.t.view(np.uint32) == b.t.view(np.uint32)).all()
+    assert (a.rgba == b.rgba).all() and (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
+    for k in ("rays_primary", "rays_shadow", "rays_secondary"):
+        assert a.stats[k] == b.stats[k]
+    host.close(); dev.close()
+
+
+def test_gpu_build_with_spheres_and_slivers(pkg, capi, scene_dir):
+    """Mixed leaves (analytic spheres beside triangles) and sliver faces, whose boxes are widened from their octree
+    leaves: frames of both builds are identical."""
+    g = load_golden("hf32_point_256x144")
+    verts, fn, vn, mid, mats = [np.array(a) for a in scene_arrays("hf32_point_256x144", pkg, scene_dir)]
+    verts = verts.reshape(-1, 3, 3).copy()
+    rng = np.random.default_rng(11)
+    for f in rng.choice(len(verts), 40, replace=False):  # collapse 40 faces to slivers / points
+        verts[f, 2] = verts[f, 0] + (verts[f, 1] - verts[f, 0]) * np.float32(rng.uniform(0, 1)) + np.float32(rng.choice([0, 1e-9]))
+    mn, mx = verts.reshape(-1, 3).min(0), verts.reshape(-1, 3).max(0)
+    S = 50
+    spheres = np.concatenate([(mn + (mx - mn) * rng.uniform(0, 1, (S, 3))), rng.uniform(0.01, 0.04, (S, 1))], 1).astype(np.float32)
+    sphere_mat = np.zeros(S, np.int32)
+    host, dev = build_both(capi, (verts.reshape(-1, 9), fn, vn, mid, mats), None, spheres, sphere_mat)
+    assert dev.build_info()["octree"] == host.build_info()["octree"]
+    W, H = 320, 240
+    cam = capi.default_camera(W, H)
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    for area, point, depth in [(0, 1, 2), (1, 0, 1)]:
+        params = capi.make_params(W, H, area, point, depth, (3, 3))
+        a, b = host.render(cam, lights, params), dev.render(cam, lights, params)
+        assert (a.face == b.face).all() and (a.t.view(np.uint32) == b.t.view(np.uint32)).all()
+        assert (a.rgba == b.rgba).all()
+    host.close(); dev.close()
+
+
+def test_gpu_build_is_deterministic_and_fast(pkg, capi, scene_dir):
+    """Two builds of the 1 M-triangle height field give the same structures, within the build-time bar
+    (rt_scene_create <= 100 ms at 1 M triangles; the host builders take ~0.8 s)."""
+    arrays = scene_arrays("hf707_point_1920x1080_s20", pkg, scene_dir)
+    capi.init(0)
+    capi.Scene(*arrays).close()  # warm-up: context, allocator
+    a, b = capi.Scene(*arrays), capi.Scene(*arrays)
+    ia, ib = a.build_info(), b.build_info()
+    print("1M build:", ia)
+    assert ia["gpu"] and ib["gpu"]
+    na, ta = a.debug_bvh()
+    nb, tb = b.debug_bvh()
+    assert np.array_equal(na.view(np.uint32), nb.view(np.uint32)) and np.array_equal(ta, tb)
+    assert ia["octree"] == ib["octree"] and ia["sah"] == ib["sah"]
+    assert min(ia["build_ms"], ib["build_ms"]) <= 100.0
+    a.close(); b.close()

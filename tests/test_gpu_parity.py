@@ -222,3 +222,36 @@ def test_c4_benchmark_config_vs_port(pkg, capi, oracle_mod):
           f"{int(err.max())}, float RGB bit-identical {same_f32:.6f}, levels {fr.stats['levels']}, secondary rays {fr.stats['rays_secondary']}")
     assert err.max() <= 1 and (err == 0).mean() >= 0.9999
     scene.close()
+
+
+@pytest.mark.parametrize("case", ["hf224_area_d5_g4_3840x2160_s24", "hf224m_area_d5_g4_3840x2160_s48", "hf707_point_1920x1080_s20",
+                                  "gallery_area_200x150", "dodge_area_rot_400x300"])
+@pytest.mark.parametrize("refill,quorum", [(8, 16), (1, 33), (24, 4)])
+def test_streaming_shadow_kernel_matches_reference_golden(case, refill, quorum, pkg, capi, scene_dir):
+    """k_shadow_stream (lane-level replacement of finished shadow rays) must decide every visibility exactly like
+    k_shadow: the goldens of the traversal-heavy scenes again, for several refill thresholds."""
+    g = load_golden(case)
+    verts, fn, vn, mid, mats = scene_arrays(case, pkg, scene_dir)
+    capi.init(0)
+    scene = capi.Scene(verts, fn, vn, mid, mats, g["model_matrix"])
+    cp = case_params(g)
+    cam = capi.make_camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    lights = capi.Lights(g["lights"], g["light_color"])
+    params = capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], cp["max_depth"], cp["grid"])
+    try:
+        capi.set_option("fused_frame", 0)
+        ref = scene.render(cam, lights, params)
+        capi.set_option("shadow_stream", 1)
+        capi.set_option("refill_min_lanes", refill)
+        capi.set_option("leaf_quorum", quorum)
+        fr = scene.render(cam, lights, params)
+    finally:
+        capi.set_option("shadow_stream", 0); capi.set_option("refill_min_lanes", 8); capi.set_option("leaf_quorum", 16)
+        capi.set_option("fused_frame", 2)
+    assert (fr.rgba == ref.rgba).all() and (fr.face == ref.face).all()
+    assert (fr.rgb.view(np.uint32) == ref.rgb.view(np.uint32)).all()
+    assert fr.stats["rays_shadow"] == ref.stats["rays_shadow"]
+    px, py = g["pxy"][:, 0], g["pxy"][:, 1]
+    err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - quant(g["rgb"])).max(-1)
+    assert (err <= 1).mean() >= 0.999
+    scene.close()
