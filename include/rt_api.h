@@ -204,12 +204,12 @@ int rt_bvh_check(const RtSceneDesc *desc, int32_t leaf_size, int64_t out[6]);
 /* Which builder made the scene's acceleration structures and what came out.  Scenes of at least
  * "gpu_build_min_prims" primitives (rt_set_option, default 20000; option "gpu_build": 0 never, 1 from 64 primitives on,
  * 2 = that threshold) are built ON THE DEVICE: the reference octree (BoxTree::BoxTree / split / clasifyFace,
- * src/boxTree.cpp:11-31, 88-147, 203-336) level by level, the BVH by parallel locally-ordered clustering over a Morton
- * order, the primitive soup and the shading table by one thread per primitive (csrc/rt_build.cuh).  out[16] =
+ * src/boxTree.cpp:11-31, 88-147, 203-336) level by level, the BVH top down by binned surface-area-heuristic
+ * splits over a Morton order (one launch per tree level), the primitive soup and the shading table by one thread per primitive (csrc/rt_build.cuh).  out[16] =
  * built on the GPU (0/1), BVH pair nodes, leaves, depth, 1000 x SAH cost (the definition of rt_bvh_check),
  * octree leaves / inner nodes / face references / largest leaf (the numbers of rt_ref_octree_stats),
- * build microseconds: total, input upload, octree, Morton sort, clustering, emit + bake; 1000 x octree levels +
- * clustering rounds. */
+ * build microseconds: total, input upload, octree, Morton sort, BVH splits, emit + bake; 1000 x octree levels +
+ * BVH levels. */
 int rt_scene_build_info(const RtScene *scene, int64_t out[16]);
 /* debug / test access to the flattened BVH (host copies): nodes [n_nodes][16] floats as uploaded,
  * tri_face [n_tris] original face id of each soup slot */

@@ -362,7 +362,7 @@ class Scene:
         return dict(gpu=bool(o[0]), nodes=int(o[1]), leaves=int(o[2]), depth=int(o[3]), sah=o[4] / 1000.0,
                     octree=dict(leaves=int(o[5]), inner=int(o[6]), refs=int(o[7]), max_leaf=int(o[8])),
                     build_ms=o[9] / 1000.0, upload_ms=o[10] / 1000.0, octree_ms=o[11] / 1000.0, sort_ms=o[12] / 1000.0,
-                    cluster_ms=o[13] / 1000.0, emit_ms=o[14] / 1000.0, octree_levels=int(o[15] // 1000), cluster_rounds=int(o[15] % 1000))
+                    bvh_ms=o[13] / 1000.0, emit_ms=o[14] / 1000.0, octree_levels=int(o[15] // 1000), bvh_levels=int(o[15] % 1000))
 
     def debug_bvh(self):
         inf = self.info()

@@ -182,8 +182,8 @@ struct RtScene {
   double sah_cost = 0.0;            // bvh_builder.cpp's definition, for either builder
   bool built_on_gpu = false;        // rt_gpu_build.inl
   DevBuf prim_order;                // GPU build: soup slot -> primitive id (host copy fetched on demand)
-  float build_phase_ms[5] = {0, 0, 0, 0, 0};  // GPU build: upload, octree, sort, clustering, emit + bake
-  int build_rounds[2] = {0, 0};     // GPU build: octree levels, clustering rounds
+  float build_phase_ms[5] = {0, 0, 0, 0, 0};  // GPU build: upload, octree, sort, BVH splits, emit + bake
+  int build_rounds[2] = {0, 0};     // GPU build: octree levels, BVH levels
   // per-frame workspace
   std::vector<LevelStore> levels;
   DevBuf frame_counts;    // FrameCounts
@@ -691,7 +691,7 @@ extern "C" int rt_scene_create(const RtSceneDesc *desc, RtScene **out) {
     bool too_deep = false;
     if ((rc = gpu_build_scene(desc, out, &too_deep))) return rc;
     if (!too_deep) return RT_OK;
-    // (a clustered tree deeper than the traversal stack: the host builder bounds its depth by construction)
+    // (never taken: both builders guard their depth)
   }
   HostBake hb;
   bake_scene(desc, hb);

@@ -12,12 +12,9 @@
 //      (face, octant) pairs; octants are then classified (empty / leaf / split / "exactly capacity": hidden) exactly as
 //      BoxTree::split does, leaves append their (face, leaf) references, split octants form the next level;
 //   2. primitive boxes (sliver faces widened from their octree leaves, see rt_api.cu), 63-bit Morton codes, radix sort;
-//   3. BVH by PLOC (parallel locally-ordered clustering, Meister & Bittner 2017): every cluster looks for the
-//      neighbour within +-kPlocRadius positions of the Morton order whose union with it has the smallest area;
-//      mutual nearest neighbours merge; repeat until one cluster is left.  Unlike a plain Morton-split LBVH this
-//      bottom-up agglomeration gives trees of SAH quality;
-//   4. top-down pass in reverse creation order: first primitive slot and depth of every node (leaf order = soup
-//      order); subtrees of at most `leaf` primitives become leaves; 64-byte pair nodes as bvh_builder.hpp defines them;
+//   3. BVH top down by binned surface-area-heuristic splits (the algorithm of host/bvh_builder.cpp), one launch per
+//      tree level, every node split by its own thread block or warp with its bins in shared memory;
+//   4. 64-byte pair nodes as bvh_builder.hpp defines them, in breadth-first order;
 //   5. bake: primitive soup (80 B), shading table (112 B) with the host's expressions.
 #pragma once
 
@@ -358,137 +355,277 @@ __global__ void k_morton(const float *__restrict__ boxes, const int N, const Bou
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3. PLOC
+// 3. BVH: binned surface-area-heuristic splits, top down, one level per launch
+//
+// The algorithm of host/bvh_builder.cpp (16 centroid bins per axis, cost = area x count, median fall-back, depth
+// guard), so the tree has the host tree's quality; what changes is who does the work: every node of a level is split
+// by its own group of threads -- a 1024-thread block for nodes of more than kSahBigNode primitives, a single warp
+// otherwise -- and all nodes of a level are split by one launch.  A group makes three passes over its node's
+// primitives (centroid bounds; bins; stable partition into the other index buffer) with its bins in shared memory.
+// Primitives arrive in Morton order, so the lanes of a warp mostly fall into one or two bins: lanes with the same
+// bin are combined with match / redux before the shared-memory atomics.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPlocRadius = 16;
+constexpr int kSahBins = 16;
+constexpr int kSahMaxDepth = 60;    // device traversal stack holds 64 entries (bvh_builder.cpp kMaxDepth)
+constexpr int kSahBigNode = 2048;
 
-struct BuildNodes {      // binary tree under construction: nodes 0..N-1 are the leaves (sorted primitives)
-  float *box;            // [2N][6]
-  int32_t *left, *right; // children (-1 for leaves)
-  int32_t *count;        // primitives below
-  int32_t *first;        // first soup slot (top-down pass)
-  int32_t *depth;
+struct SahNodes {   // 2N entries; node 0 is the root, children are created in pairs (right = left + 1)
+  int32_t *lo, *cnt, *left, *depth;
+  float *box;       // [6] bounds of the node's (padded) primitive boxes, written by its parent
 };
 
-__global__ void k_ploc_init(const float *__restrict__ prim_boxes, const int32_t *__restrict__ sorted_ids, const int N, BuildNodes bn,
-                            int32_t *clusters) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const int p = sorted_ids[i];
-  for (int a = 0; a < 6; ++a) bn.box[(size_t)i * 6 + a] = prim_boxes[(size_t)p * 6 + a];
-  bn.left[i] = -1; bn.right[i] = -1; bn.count[i] = 1;
-  clusters[i] = i;
-}
+struct SahShared {
+  unsigned int cb[6];
+  unsigned int bin_box[3][kSahBins][6];
+  int bin_cnt[3][kSahBins];
+  unsigned int child_box[2][6];
+  int axis, split, nleft, fallback, done_l, done_r;
+  float cmin[3], scale[3];
+};
 
-__device__ __forceinline__ float union_half_area(const float *a, const float *b) {
-  const float dx = fmaxf(a[3], b[3]) - fminf(a[0], b[0]), dy = fmaxf(a[4], b[4]) - fminf(a[1], b[1]),
-              dz = fmaxf(a[5], b[5]) - fminf(a[2], b[2]);
+__device__ __forceinline__ float sah_half_area(const float *mn, const float *mx) {
+  const float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+  if (dx < 0 || dy < 0 || dz < 0) return 0.f;
   return dx * dy + dy * dz + dz * dx;
 }
-
-// nearest neighbour of every cluster within the search radius (ties: the lower position)
-__global__ void k_ploc_nn(const int32_t *__restrict__ clusters, const int n, const float *__restrict__ box, int32_t *nn) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float bi[6];
-  const float *pb = box + (size_t)clusters[i] * 6;
-  for (int a = 0; a < 6; ++a) bi[a] = pb[a];
-  const int lo = max(0, i - kPlocRadius), hi = min(n - 1, i + kPlocRadius);
-  float best = 3.4e38f;
-  int bj = -1;
-  for (int j = lo; j <= hi; ++j) {
-    if (j == i) continue;
-    const float A = union_half_area(bi, box + (size_t)clusters[j] * 6);
-    if (A < best) { best = A; bj = j; }
-  }
-  nn[i] = bj;
+__device__ __forceinline__ int sah_bin(float c, float cmin, float scale) {
+  int b = (int)((c - cmin) * scale);
+  return b < 0 ? 0 : (b >= kSahBins ? kSahBins - 1 : b);
 }
 
-// flags: merge[i] = 1 if position i creates a node (mutual pair, lower position), keep[i] = 0 if it vanishes
-__global__ void k_ploc_flags(const int32_t *__restrict__ nn, const int n, int32_t *merge, int32_t *keep, int *n_merged) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool m = false;
-  if (i < n) {
-    const int j = nn[i];
-    const bool mutual = j >= 0 && nn[j] == i;
-    m = mutual && i < j;
-    merge[i] = m ? 1 : 0;
-    keep[i] = (mutual && i > j) ? 0 : 1;
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sah_split(const int32_t *__restrict__ sel, const int32_t *__restrict__ act,
+                                                     const int child_base, const int leaf, const float *__restrict__ pbox,
+                                                     const int32_t *__restrict__ in, int32_t *out, int32_t *final_order, SahNodes nd) {
+  __shared__ SahShared s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int k = sel[blockIdx.x], node = act[k];
+  const int lo = nd.lo[node], cnt = nd.cnt[node], depth = nd.depth[node];
+  const unsigned FULL = 0xffffffffu;
+  // ---- init ----
+  for (int i = tid; i < 3 * kSahBins * 6; i += BLOCK) {
+    const int v = i % 6;
+    (&s.bin_box[0][0][0])[i] = v < 3 ? 0xffffffffu : 0u;  // ordered encodings: min slots start at +max, max slots at -max
   }
-  const unsigned b = __ballot_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_merged, __popc(b));
+  for (int i = tid; i < 3 * kSahBins; i += BLOCK) (&s.bin_cnt[0][0])[i] = 0;
+  if (tid < 6) s.cb[tid] = tid < 3 ? 0xffffffffu : 0u;
+  if (tid < 12) (&s.child_box[0][0])[tid] = (tid % 6) < 3 ? 0xffffffffu : 0u;
+  if (tid == 0) { s.done_l = 0; s.done_r = 0; }
+  __syncthreads();
+  // ---- pass 1: centroid bounds ----
+  {
+    unsigned int mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+    for (int i = tid; i < cnt; i += BLOCK) {
+      const float *b = pbox + (size_t)in[lo + i] * 6;
+      for (int a = 0; a < 3; ++a) {
+        const unsigned int c = f2ord(0.5f * (b[a] + b[3 + a]));
+        mn[a] = min(mn[a], c); mx[a] = max(mx[a], c);
+      }
+    }
+    for (int a = 0; a < 3; ++a) {
+      const unsigned int wmn = __reduce_min_sync(FULL, mn[a]), wmx = __reduce_max_sync(FULL, mx[a]);
+      if (lane == 0) { atomicMin(&s.cb[a], wmn); atomicMax(&s.cb[3 + a], wmx); }
+    }
+  }
+  __syncthreads();
+  if (tid < 3) {
+    const float cmin = ord2f(s.cb[tid]), cext = ord2f(s.cb[3 + tid]) - cmin;
+    s.cmin[tid] = cmin;
+    s.scale[tid] = cext > 0.f ? (float)kSahBins / cext : 0.f;  // 0: the axis offers no split
+  }
+  int need = 0;
+  while ((1 << need) < cnt) ++need;
+  const bool use_sah = depth + need < kSahMaxDepth - 1;
+  __syncthreads();
+  // ---- pass 2: bins ----
+  if (use_sah) {
+    for (int base = 0; base < cnt; base += BLOCK) {
+      const int i = base + tid;
+      const bool valid = i < cnt;
+      float bx[6] = {0, 0, 0, 0, 0, 0};
+      if (valid) {
+        const float *b = pbox + (size_t)in[lo + i] * 6;
+        for (int v = 0; v < 6; ++v) bx[v] = b[v];
+      }
+      unsigned int ob[6];
+      for (int v = 0; v < 6; ++v) ob[v] = f2ord(bx[v]);
+      for (int a = 0; a < 3; ++a) {
+        const float scale = s.scale[a];
+        if (!(scale > 0.f)) continue;  // (uniform across the block)
+        const int bin = valid ? sah_bin(0.5f * (bx[a] + bx[3 + a]), s.cmin[a], scale) : 64 + lane;
+        const unsigned m = __match_any_sync(FULL, bin);
+        unsigned int r[6];
+        for (int v = 0; v < 3; ++v) { r[v] = __reduce_min_sync(m, ob[v]); r[3 + v] = __reduce_max_sync(m, ob[3 + v]); }
+        if (valid && lane == __ffs(m) - 1) {
+          atomicAdd(&s.bin_cnt[a][bin], __popc(m));
+          for (int v = 0; v < 3; ++v) { atomicMin(&s.bin_box[a][bin][v], r[v]); atomicMax(&s.bin_box[a][bin][3 + v], r[3 + v]); }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- split selection (bvh_builder.cpp sah_partition: axes in order, first strictly better candidate wins) ----
+  if (tid == 0) {
+    float best_cost = 3.402823466e+38f;
+    int best_axis = -1, best_split = -1, best_left = 0;
+    if (use_sah) {
+      for (int a = 0; a < 3; ++a) {
+        if (!(s.scale[a] > 0.f)) continue;
+        float right_area[kSahBins];
+        int right_cnt[kSahBins];
+        float amn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, amx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+        int c = 0;
+        for (int b = kSahBins - 1; b > 0; --b) {
+          if (s.bin_cnt[a][b] > 0)
+            for (int v = 0; v < 3; ++v) { amn[v] = fminf(amn[v], ord2f(s.bin_box[a][b][v])); amx[v] = fmaxf(amx[v], ord2f(s.bin_box[a][b][3 + v])); }
+          c += s.bin_cnt[a][b];
+          right_area[b] = sah_half_area(amn, amx); right_cnt[b] = c;
+        }
+        float lmn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, lmx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+        int lc = 0;
+        for (int b = 0; b < kSahBins - 1; ++b) {
+          if (s.bin_cnt[a][b] > 0)
+            for (int v = 0; v < 3; ++v) { lmn[v] = fminf(lmn[v], ord2f(s.bin_box[a][b][v])); lmx[v] = fmaxf(lmx[v], ord2f(s.bin_box[a][b][3 + v])); }
+          lc += s.bin_cnt[a][b];
+          if (lc == 0 || right_cnt[b + 1] == 0) continue;
+          const float cost = sah_half_area(lmn, lmx) * (float)lc + right_area[b + 1] * (float)right_cnt[b + 1];
+          if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = b; best_left = lc; }
+        }
+      }
+    }
+    s.fallback = best_axis < 0 ? 1 : 0;
+    s.axis = best_axis < 0 ? 0 : best_axis;
+    s.split = best_split;
+    s.nleft = best_axis < 0 ? cnt / 2 : best_left;  // no usable split: halve the (Morton-ordered) range
+  }
+  __syncthreads();
+  // ---- pass 3: stable partition into the other buffer, child boxes ----
+  const int axis = s.axis, split = s.split, nleft = s.nleft;
+  const bool fallback = s.fallback != 0;
+  const float cmin = s.cmin[axis], scale = s.scale[axis];
+  const bool leaf_l = nleft <= leaf, leaf_r = cnt - nleft <= leaf;
+  unsigned int cb[2][6];
+  for (int c = 0; c < 2; ++c)
+    for (int v = 0; v < 6; ++v) cb[c][v] = v < 3 ? 0xffffffffu : 0u;
+  for (int base = 0; base < cnt; base += BLOCK) {
+    const int i = base + tid;
+    const bool valid = i < cnt;
+    int p = 0;
+    bool left = false;
+    if (valid) {
+      p = in[lo + i];
+      const float *b = pbox + (size_t)p * 6;
+      left = fallback ? (i < nleft) : (sah_bin(0.5f * (b[axis] + b[3 + axis]), cmin, scale) <= split);
+      const int c = left ? 0 : 1;
+      for (int v = 0; v < 3; ++v) { cb[c][v] = min(cb[c][v], f2ord(b[v])); cb[c][3 + v] = max(cb[c][3 + v], f2ord(b[3 + v])); }
+    }
+    int rank_l, total_l;
+    if constexpr (BLOCK == 32) {
+      const unsigned m = __ballot_sync(FULL, left);
+      rank_l = __popc(m & ((1u << lane) - 1u)); total_l = __popc(m);
+    } else {
+      typedef cub::BlockScan<int, BLOCK> Scan;
+      __shared__ typename Scan::TempStorage tmp;
+      Scan(tmp).ExclusiveSum(left ? 1 : 0, rank_l, total_l);
+    }
+    if (valid) {
+      const int dst = left ? lo + s.done_l + rank_l : lo + nleft + s.done_r + (tid - rank_l);
+      out[dst] = p;
+      if (left ? leaf_l : leaf_r) final_order[dst] = p;
+    }
+    __syncthreads();
+    if (tid == 0) { s.done_l += total_l; s.done_r += min(BLOCK, cnt - base) - total_l; }
+    __syncthreads();
+  }
+  for (int c = 0; c < 2; ++c)
+    for (int v = 0; v < 6; ++v) {
+      const unsigned int w = v < 3 ? __reduce_min_sync(FULL, cb[c][v]) : __reduce_max_sync(FULL, cb[c][v]);
+      if (lane == 0) { if (v < 3) atomicMin(&s.child_box[c][v], w); else atomicMax(&s.child_box[c][v], w); }
+    }
+  __syncthreads();
+  if (tid < 2) {
+    const int c = tid, id = child_base + 2 * k + c;
+    nd.lo[id] = c == 0 ? lo : lo + nleft;
+    nd.cnt[id] = c == 0 ? nleft : cnt - nleft;
+    nd.depth[id] = depth + 1;
+    nd.left[id] = -1;
+    for (int v = 0; v < 6; ++v) nd.box[(size_t)id * 6 + v] = ord2f(s.child_box[c][v]);
+    if (c == 0) nd.left[node] = id;
+  }
 }
 
-__global__ void k_ploc_merge(const int32_t *__restrict__ clusters, const int32_t *__restrict__ nn, const int n,
-                             const int32_t *__restrict__ merge, const int32_t *__restrict__ merge_pos, const int32_t *__restrict__ keep,
-                             const int32_t *__restrict__ keep_pos, const int next_node, BuildNodes bn, int32_t *clusters_out) {
+// the children created by one level: which of them are split next (in id order: deterministic node numbering) ...
+__global__ void k_sah_flags(const int first, const int n, const SahNodes nd, const int leaf, int32_t *flag_act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag_act[i] = nd.cnt[first + i] > leaf ? 1 : 0;
+}
+__global__ void k_sah_lists(const int first, const int n, const int32_t *__restrict__ flag_act, const int32_t *__restrict__ pos_act,
+                            int32_t *act, int32_t *totals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (!keep[i]) return;
-  int c = clusters[i];
-  if (merge[i]) {
-    const int l = c, r = clusters[nn[i]];
-    const int id = next_node + merge_pos[i];
-    const float *bl = bn.box + (size_t)l * 6, *br = bn.box + (size_t)r * 6;
-    float *bo = bn.box + (size_t)id * 6;
-    for (int a = 0; a < 3; ++a) { bo[a] = fminf(bl[a], br[a]); bo[3 + a] = fmaxf(bl[3 + a], br[3 + a]); }
-    bn.left[id] = l; bn.right[id] = r;
-    bn.count[id] = bn.count[l] + bn.count[r];
-    c = id;
-  }
-  clusters_out[keep_pos[i]] = c;
+  if (flag_act[i]) act[pos_act[i]] = first + i;
+  if (i == n - 1) totals[0] = pos_act[i] + flag_act[i];
+}
+// ... and by which kind of group: rank k of the active list -> list of the big / of the small nodes
+__global__ void k_sah_kind(const int32_t *__restrict__ act, const int n_act, const SahNodes nd, int32_t *flag_big, int32_t *flag_small) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_act) return;
+  const bool big = nd.cnt[act[k]] > kSahBigNode;
+  flag_big[k] = big ? 1 : 0;
+  flag_small[k] = big ? 0 : 1;
+}
+__global__ void k_sah_select(const int n_act, const int32_t *__restrict__ flag_big, const int32_t *__restrict__ pos_big,
+                             const int32_t *__restrict__ pos_small, int32_t *sel_big, int32_t *sel_small, int32_t *totals) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_act) return;
+  if (flag_big[k]) sel_big[pos_big[k]] = k; else sel_small[pos_small[k]] = k;
+  if (k == n_act - 1) { totals[1] = pos_big[k] + flag_big[k]; totals[2] = pos_small[k] + (flag_big[k] ? 0 : 1); }
+}
+__global__ void k_sah_root(SahNodes nd, const int N, int32_t *act) {
+  nd.lo[0] = 0; nd.cnt[0] = N; nd.depth[0] = 0; nd.left[0] = -1;
+  act[0] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4. top-down pass, pair nodes
+// 4. pair nodes
 // ---------------------------------------------------------------------------------------------
-__global__ void k_topdown(const int id_begin, const int id_end, BuildNodes bn, int32_t *max_depth) {
-  const int id = id_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= id_end) return;
-  const int l = bn.left[id], r = bn.right[id];
-  const int f = bn.first[id], d = bn.depth[id];
-  bn.first[l] = f; bn.first[r] = f + bn.count[l];
-  bn.depth[l] = d + 1; bn.depth[r] = d + 1;
-  atomicMax(max_depth, d + 1);
+__global__ void k_pair_flags(const int n_nodes, const SahNodes nd, const int leaf, int32_t *flag) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < n_nodes) flag[id] = nd.cnt[id] > leaf ? 1 : 0;
 }
-__global__ void k_leaf_order(const int N, const BuildNodes bn, const int32_t *__restrict__ sorted_ids, int32_t *prim_order) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) prim_order[bn.first[i]] = sorted_ids[i];
-}
-// inner[k] = 1 for tree nodes that become pair nodes (more than `leaf` primitives), in REVERSE id order (root first)
-__global__ void k_pair_flags(const int N, const int n_nodes, const BuildNodes bn, const int leaf, int32_t *flag) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_nodes - N) return;
-  const int id = n_nodes - 1 - k;
-  flag[k] = bn.count[id] > leaf ? 1 : 0;
-}
-__global__ void k_emit_pairs(const int N, const int n_nodes, const BuildNodes bn, const int leaf, const int T,
-                             const int32_t *__restrict__ flag, const int32_t *__restrict__ pos, const int32_t *__restrict__ prim_order,
-                             float4 *nodes_out, unsigned int *n_leaves, double *sah) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_emit_pairs(const int n_nodes, const SahNodes nd, const int leaf, const int T, const int32_t *__restrict__ flag,
+                             const int32_t *__restrict__ pos, const int32_t *__restrict__ prim_order, float4 *nodes_out,
+                             unsigned int *n_leaves, int32_t *max_depth, double *sah) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
   // surface-area-heuristic cost with the host builder's definition (bvh_builder.cpp): inner boxes + leaf boxes x count
   double cost = 0.0;
   unsigned leaves = 0;
-  if (k < n_nodes - N && flag[k]) {
-    const int id = n_nodes - 1 - k;
-    const int ch[2] = {bn.left[id], bn.right[id]};
+  int deepest = 0;
+  if (id < n_nodes && flag[id]) {
+    const int ch[2] = {nd.left[id], nd.left[id] + 1};
     int code[2];
-    cost = (double)union_half_area(bn.box + (size_t)id * 6, bn.box + (size_t)id * 6);
+    const float *b0 = nd.box + (size_t)ch[0] * 6, *b1 = nd.box + (size_t)ch[1] * 6;
+    {
+      float mn[3], mx[3];
+      for (int v = 0; v < 3; ++v) { mn[v] = fminf(b0[v], b1[v]); mx[v] = fmaxf(b0[3 + v], b1[3 + v]); }
+      cost = (double)sah_half_area(mn, mx);
+    }
     for (int c = 0; c < 2; ++c) {
       const int cid = ch[c];
-      if (bn.count[cid] > leaf) {
-        code[c] = pos[n_nodes - 1 - cid];
+      if (nd.cnt[cid] > leaf) {
+        code[c] = pos[cid];
       } else {
-        const int first = bn.first[cid], cnt = bn.count[cid];
+        const int first = nd.lo[cid], cnt = nd.cnt[cid];
         bool mixed = false;
-        for (int s = first; s < first + cnt; ++s) mixed |= prim_order[s] >= T;
+        for (int q = first; q < first + cnt; ++q) mixed |= prim_order[q] >= T;
         code[c] = ~((first << 5) | ((mixed ? 1 : 0) << 4) | (cnt - 1));
         leaves++;
-        cost += (double)union_half_area(bn.box + (size_t)cid * 6, bn.box + (size_t)cid * 6) * cnt;
+        deepest = max(deepest, nd.depth[cid]);
+        const float *b = nd.box + (size_t)cid * 6;
+        cost += (double)sah_half_area(b, b + 3) * cnt;
       }
     }
-    const float *b0 = bn.box + (size_t)ch[0] * 6, *b1 = bn.box + (size_t)ch[1] * 6;
-    float4 *o = nodes_out + (size_t)pos[k] * 4;
+    float4 *o = nodes_out + (size_t)pos[id] * 4;
     o[0] = make_float4(b0[0], b0[3], b0[1], b0[4]);
     o[1] = make_float4(b1[0], b1[3], b1[1], b1[4]);
     o[2] = make_float4(b0[2], b0[5], b1[2], b1[5]);
@@ -497,9 +634,10 @@ __global__ void k_emit_pairs(const int N, const int n_nodes, const BuildNodes bn
   for (int off = 16; off > 0; off >>= 1) {
     cost += __shfl_down_sync(0xffffffffu, cost, off);
     leaves += __shfl_down_sync(0xffffffffu, leaves, off);
+    deepest = max(deepest, __shfl_down_sync(0xffffffffu, deepest, off));
   }
   if ((threadIdx.x & 31) == 0) {
-    if (leaves) atomicAdd(n_leaves, leaves);
+    if (leaves) { atomicAdd(n_leaves, leaves); atomicMax(max_depth, deepest); }
     if (cost != 0.0) atomicAdd(sah, cost);
   }
 }

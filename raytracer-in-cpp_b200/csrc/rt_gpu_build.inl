@@ -3,8 +3,8 @@
 // rt_scene_create for large scenes: the triangle arrays are uploaded once and everything the frame kernels read -- the
 // reference octree used as candidate filter (BoxTree::BoxTree / split / clasifyFace, src/boxTree.cpp:11-31, 88-147,
 // 203-336 of the reference), the BVH, the 80-byte primitive soup and the 112-byte shading table -- is computed on the
-// device.  The host only sequences the launches: one 32-byte read-back per octree level and a 4-byte one per PLOC
-// round.  Same outputs as the host bake (bake_scene) except for the shape of the BVH, which never changes a frame:
+// device.  The host only sequences the launches: one 32-byte read-back per octree level and two small ones per
+// BVH level.  Same outputs as the host bake (bake_scene) except for the shape of the BVH, which never changes a frame:
 // nearest hits are ordered by (t, face id) and shadow queries are boolean, whatever the traversal order.
 
 namespace {
@@ -47,10 +47,10 @@ int exclusive_scan(BuildArena &scratch, const int32_t *in, int32_t *out, int n) 
   return RT_OK;
 }
 
-struct GpuBuildTimes { float upload_ms = 0, octree_ms = 0, sort_ms = 0, ploc_ms = 0, emit_ms = 0, total_ms = 0; int ploc_rounds = 0, oct_levels = 0; };
+struct GpuBuildTimes { float upload_ms = 0, octree_ms = 0, sort_ms = 0, bvh_ms = 0, emit_ms = 0, total_ms = 0; int bvh_levels = 0, oct_levels = 0; };
 
 // Returns RT_OK with *out set, or an error; *too_deep is set (and RT_OK returned with *out == nullptr) when the
-// clustered tree is deeper than the traversal stack allows -- the caller then takes the host builder, which bounds
+// tree is deeper than the traversal stack allows -- the caller then takes the host builder, which bounds
 // its depth by construction.
 int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   using namespace rtb;
@@ -271,78 +271,83 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   const int32_t *sorted_ids = ids.Current();
   tm.sort_ms = ms_since(t_sort);
 
-  // ---- 3. PLOC ----
-  const auto t_ploc = clk::now();
-  BuildNodes bn;
+  // ---- 3. BVH: binned SAH splits, one launch pair (big nodes / small nodes) per tree level ----
+  const auto t_bvh = clk::now();
+  const int leaf = std::max(1, std::min(16, g_opt_leaf));
   const size_t NN = (size_t)2 * N;
-  bn.box = perm.get<float>(NN * 6);
-  bn.left = perm.get<int32_t>(NN); bn.right = perm.get<int32_t>(NN); bn.count = perm.get<int32_t>(NN);
-  bn.first = perm.get<int32_t>(NN); bn.depth = perm.get<int32_t>(NN);
-  if (!bn.box || !bn.left || !bn.right || !bn.count || !bn.first || !bn.depth) return fail(RT_ERR_CUDA, "GPU build: node arrays");
-  RT_ARENA(cl_a, perm, int32_t, (size_t)N);
-  RT_ARENA(cl_b, perm, int32_t, (size_t)N);
-  RT_ARENA(nn, perm, int32_t, (size_t)N);
-  RT_ARENA(merge, perm, int32_t, (size_t)N);
-  RT_ARENA(keep, perm, int32_t, (size_t)N);
-  RT_ARENA(merge_pos, perm, int32_t, (size_t)N);
-  RT_ARENA(keep_pos, perm, int32_t, (size_t)N);
-  RT_ARENA(d_cnt, perm, int, 4);
-  k_ploc_init<<<cdiv((size_t)N, 256), 256>>>(d_boxes, sorted_ids, N, bn, cl_a);
-  std::vector<std::pair<int, int>> rounds;  // node-id range created by each round
-  {
-    int n = N, next_node = N;
-    int32_t *cin = cl_a, *cout = cl_b;
-    while (n > 1) {
-      scratch.reset();
-      CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, 0));
-      k_ploc_nn<<<cdiv((size_t)n, 128), 128>>>(cin, n, bn.box, nn);
-      k_ploc_flags<<<cdiv((size_t)n, 256), 256>>>(nn, n, merge, keep, d_cnt);
-      if ((rc = exclusive_scan(scratch, merge, merge_pos, n)) || (rc = exclusive_scan(scratch, keep, keep_pos, n))) return rc;
-      k_ploc_merge<<<cdiv((size_t)n, 256), 256>>>(cin, nn, n, merge, merge_pos, keep, keep_pos, next_node, bn, cout);
-      int m = 0;
-      CUDA_TRY(cudaMemcpy(&m, d_cnt, 4, cudaMemcpyDeviceToHost));
-      if (m <= 0) return fail(RT_ERR_CUDA, "GPU build: clustering made no progress at %d clusters", n);
-      rounds.push_back({next_node, next_node + m});
-      next_node += m;
-      n -= m;
-      std::swap(cin, cout);
-      ++tm.ploc_rounds;
-    }
-  }
-  tm.ploc_ms = ms_since(t_ploc);
-
-  // ---- 4. top-down: soup order, depth, pair nodes ----
-  const auto t_emit = clk::now();
-  const int n_tree = 2 * N - 1, root = n_tree - 1;
-  RT_ARENA(d_depth, perm, int32_t, 1);
-  CUDA_TRY(cudaMemsetAsync(d_depth, 0, 4, 0));
-  CUDA_TRY(cudaMemsetAsync(bn.first + root, 0, 4, 0));
-  CUDA_TRY(cudaMemsetAsync(bn.depth + root, 0, 4, 0));
-  for (auto it = rounds.rbegin(); it != rounds.rend(); ++it)
-    k_topdown<<<cdiv((size_t)(it->second - it->first), 256), 256>>>(it->first, it->second, bn, d_depth);
-  int tree_depth = 0;
-  CUDA_TRY(cudaMemcpy(&tree_depth, d_depth, 4, cudaMemcpyDeviceToHost));
-  if (tree_depth > RT_STACK_SIZE - 6) { *too_deep = true; return RT_OK; }
+  SahNodes nd;
+  nd.lo = perm.get<int32_t>(NN); nd.cnt = perm.get<int32_t>(NN); nd.left = perm.get<int32_t>(NN); nd.depth = perm.get<int32_t>(NN);
+  nd.box = perm.get<float>(NN * 6);
+  if (!nd.lo || !nd.cnt || !nd.left || !nd.depth || !nd.box) return fail(RT_ERR_CUDA, "GPU build: node arrays");
   if ((rc = sc->prim_order.reserve((size_t)N * 4))) return rc;
   int32_t *prim_order = sc->prim_order.as<int32_t>();
-  k_leaf_order<<<cdiv((size_t)N, 256), 256>>>(N, bn, sorted_ids, prim_order);
-  const int leaf = std::max(1, std::min(16, g_opt_leaf));
-  const int n_inner = N - 1;
+  RT_ARENA(act_a, perm, int32_t, (size_t)N);
+  RT_ARENA(act_b, perm, int32_t, (size_t)N);
+  RT_ARENA(sel_big, perm, int32_t, (size_t)N);
+  RT_ARENA(sel_small, perm, int32_t, (size_t)N);
+  RT_ARENA(fl_a, perm, int32_t, (size_t)N);
+  RT_ARENA(fl_b, perm, int32_t, (size_t)N);
+  RT_ARENA(ps_a, perm, int32_t, (size_t)N);
+  RT_ARENA(ps_b, perm, int32_t, (size_t)N);
+  RT_ARENA(d_tot3, perm, int32_t, 4);
+  int n_nodes_tree = 1;
+  {
+    // index buffers: `ids` (Morton order) is level 0's input, the other half of the double buffer its output
+    int32_t *in = ids.Current(), *outb = ids.Alternate();
+    int32_t *act = act_a, *act_next = act_b;
+    k_sah_root<<<1, 1>>>(nd, N, act);
+    int n_act = 1, level_first = 0;
+    while (n_act > 0) {
+      scratch.reset();
+      // which active nodes are big (one 1024-thread block each), which small (one warp each)
+      k_sah_kind<<<cdiv((size_t)n_act, 256), 256>>>(act, n_act, nd, fl_a, fl_b);
+      if ((rc = exclusive_scan(scratch, fl_a, ps_a, n_act)) || (rc = exclusive_scan(scratch, fl_b, ps_b, n_act))) return rc;
+      k_sah_select<<<cdiv((size_t)n_act, 256), 256>>>(n_act, fl_a, ps_a, ps_b, sel_big, sel_small, d_tot3);
+      int tot[3] = {0, 0, 0};
+      CUDA_TRY(cudaMemcpy(tot, d_tot3, sizeof(tot), cudaMemcpyDeviceToHost));
+      const int n_big = tot[1], n_small = tot[2], child_base = n_nodes_tree;
+      if (n_big > 0) k_sah_split<1024><<<n_big, 1024>>>(sel_big, act, child_base, leaf, d_boxes, in, outb, prim_order, nd);
+      if (n_small > 0) k_sah_split<32><<<n_small, 32>>>(sel_small, act, child_base, leaf, d_boxes, in, outb, prim_order, nd);
+      // the children: next level's active list
+      const int n_children = 2 * n_act;
+      level_first = child_base;
+      n_nodes_tree += n_children;
+      k_sah_flags<<<cdiv((size_t)n_children, 256), 256>>>(level_first, n_children, nd, leaf, fl_a);
+      if ((rc = exclusive_scan(scratch, fl_a, ps_a, n_children))) return rc;
+      k_sah_lists<<<cdiv((size_t)n_children, 256), 256>>>(level_first, n_children, fl_a, ps_a, act_next, d_tot3);
+      CUDA_TRY(cudaMemcpy(tot, d_tot3, 4, cudaMemcpyDeviceToHost));
+      n_act = tot[0];
+      std::swap(act, act_next);
+      std::swap(in, outb);
+      ++tm.bvh_levels;
+      if (tm.bvh_levels > kSahMaxDepth + 8) return fail(RT_ERR_CUDA, "GPU build: tree deeper than %d levels", kSahMaxDepth + 8);
+    }
+  }
+  tm.bvh_ms = ms_since(t_bvh);
+
+  // ---- 4. pair nodes ----
+  const auto t_emit = clk::now();
   scratch.reset();
-  RT_ARENA(pflag, scratch, int32_t, (size_t)n_inner);
-  RT_ARENA(ppos, scratch, int32_t, (size_t)n_inner);
-  k_pair_flags<<<cdiv((size_t)n_inner, 256), 256>>>(N, n_tree, bn, leaf, pflag);
-  if ((rc = exclusive_scan(scratch, pflag, ppos, n_inner))) return rc;
+  RT_ARENA(pflag, scratch, int32_t, (size_t)n_nodes_tree);
+  RT_ARENA(ppos, scratch, int32_t, (size_t)n_nodes_tree);
+  k_pair_flags<<<cdiv((size_t)n_nodes_tree, 256), 256>>>(n_nodes_tree, nd, leaf, pflag);
+  if ((rc = exclusive_scan(scratch, pflag, ppos, n_nodes_tree))) return rc;
   int last_pos = 0, last_flag = 0;
-  CUDA_TRY(cudaMemcpy(&last_pos, ppos + n_inner - 1, 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(&last_flag, pflag + n_inner - 1, 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&last_pos, ppos + n_nodes_tree - 1, 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&last_flag, pflag + n_nodes_tree - 1, 4, cudaMemcpyDeviceToHost));
   const int n_pairs_out = last_pos + last_flag;
   if ((rc = sc->nodes.reserve((size_t)std::max(n_pairs_out, 1) * 64))) return rc;
   RT_ARENA(d_leaves, perm, unsigned, 4);
+  RT_ARENA(d_depth, perm, int32_t, 4);
   RT_ARENA(d_sah, perm, double, 2);
   CUDA_TRY(cudaMemsetAsync(d_leaves, 0, 16, 0));
+  CUDA_TRY(cudaMemsetAsync(d_depth, 0, 16, 0));
   CUDA_TRY(cudaMemsetAsync(d_sah, 0, 16, 0));
-  k_emit_pairs<<<cdiv((size_t)n_inner, 256), 256>>>(N, n_tree, bn, leaf, T, pflag, ppos, prim_order, sc->nodes.as<float4>(), d_leaves, d_sah);
+  k_emit_pairs<<<cdiv((size_t)n_nodes_tree, 256), 256>>>(n_nodes_tree, nd, leaf, T, pflag, ppos, prim_order, sc->nodes.as<float4>(), d_leaves,
+                                                       d_depth, d_sah);
+  int tree_depth = 0;
+  CUDA_TRY(cudaMemcpy(&tree_depth, d_depth, 4, cudaMemcpyDeviceToHost));
+  if (tree_depth > RT_STACK_SIZE - 3) { *too_deep = true; return RT_OK; }  // (cannot happen: the builder guards its depth)
 
   // ---- 5. bake ----
   if ((rc = sc->prims.reserve((size_t)N * 80)) || (rc = sc->shade.reserve((size_t)std::max(T, 1) * 112))) return rc;
@@ -358,9 +363,7 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   CUDA_TRY(cudaMemcpy(&n_leaves, d_leaves, 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(sah, d_sah, 8, cudaMemcpyDeviceToHost));
   {
-    float rbox[6];
-    CUDA_TRY(cudaMemcpy(rbox, bn.box + (size_t)root * 6, sizeof(rbox), cudaMemcpyDeviceToHost));
-    const double dx = rbox[3] - rbox[0], dy = rbox[4] - rbox[1], dz = rbox[5] - rbox[2];
+    const double dx = rb[3] - rb[0], dy = rb[4] - rb[1], dz = rb[5] - rb[2];
     root_area = std::max(1e-30, dx * dy + dy * dz + dz * dx);
   }
   CUDA_TRY(cudaGetLastError());
@@ -386,8 +389,8 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   tm.total_ms = ms_since(t_start);
   sc->build_ms = tm.total_ms;
   sc->build_phase_ms[0] = tm.upload_ms; sc->build_phase_ms[1] = tm.octree_ms; sc->build_phase_ms[2] = tm.sort_ms;
-  sc->build_phase_ms[3] = tm.ploc_ms; sc->build_phase_ms[4] = tm.emit_ms;
-  sc->build_rounds[0] = tm.oct_levels; sc->build_rounds[1] = tm.ploc_rounds;
+  sc->build_phase_ms[3] = tm.bvh_ms; sc->build_phase_ms[4] = tm.emit_ms;
+  sc->build_rounds[0] = tm.oct_levels; sc->build_rounds[1] = tm.bvh_levels;
   {
     std::lock_guard<std::mutex> lk(g_scenes_mu);
     g_scenes.push_back(sc);

@@ -12,7 +12,7 @@ optsets = sys.argv[2:] or [""]
 for w in wls:
     wl = bench.WORKLOADS[w]
     arrs, sp, sm = bench.workload_arrays(wl)
-    scene = capi.Scene(*arrs, None, sp, sm)
+    scene = None
     W, H = wl["w"], wl["h"]
     cam = capi.default_camera(W, H)
     lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
@@ -20,6 +20,9 @@ for w in wls:
     for o in optsets:
         for kv in o.split():
             k, v = kv.split("="); capi.set_option(k, int(v))
+        if scene is None or "build" in o or "leaf" in o:   # options that act at scene creation
+            scene = capi.Scene(*arrs, None, sp, sm)
+            print(w, f"[{o}] build", scene.build_info(), flush=True)
         capi.set_option("stats", 1)
         for _ in range(3):
             fr = scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False)
