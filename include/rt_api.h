@@ -167,7 +167,11 @@ int rt_device_name(char *buf, size_t n);
  *   per-level wavefront kernels of csrc/rt_kernels.cuh -- both paths give bit-identical frames),
  * "render_chunks" (rt_render of a scene that takes the fused kernel at any size: the frame is rendered in this many row
  *   chunks, 1..4, default 2, and the device->host copy of a chunk overlaps the rendering of the next),
- * "continue_min_lanes" (fused frame: child rays stay in their warp when at least this many of its lanes spawned one; default 8) */
+ * "continue_min_lanes" (fused frame: child rays stay in their warp when at least this many of its lanes spawned one; default 8),
+ * "donate_min_lanes" (scenes with an octree filter or spheres, shadow kernel of launches with few rays per resident warp:
+ *   lanes whose ray is finished take over pending subtrees of the lanes still traversing once at least this many lanes
+ *   are idle; 0 = never; default 12; 100 + n = in every nearest-hit and shadow launch),
+ * "gpu_build" / "gpu_build_min_prims" (see rt_scene_build_info) */
 int rt_set_option(const char *key, int value);
 void rt_default_params(RtParams *p);
 

@@ -46,7 +46,7 @@ struct DeviceState {
   int sm_count = 0;
   int grids_opt = -1;  // value of persistent_ctas_per_sm the grids below were computed for
   // persistent grid sizes: [primary rays?][stats build?][plain scene?]
-  int g_trace[2][2][2] = {}, g_shadow[2][2] = {}, g_frame[2][2] = {}, g_shadow_stream[2] = {};
+  int g_trace[2][2][2] = {}, g_shadow[2][2] = {}, g_frame[2][2] = {};
 };
 constexpr int kMaxDevices = 64;
 DeviceState g_devs[kMaxDevices];
@@ -63,10 +63,9 @@ int g_opt_gpu_build = 2;   // acceleration structures built on the device (rt_gp
                            // at least 64 primitives, 2 (default) from gpu_build_min_prims primitives on
 int g_opt_gpu_build_min = 20000;
 int g_opt_chunks = 2;      // rt_render: row chunks whose device->host copy overlaps the rendering of the next chunk
-int g_opt_shadow_stream = 0;    // K2 with lane-level ray replacement (k_shadow_stream) on scenes with an octree filter / spheres
-int g_opt_refill_min = 8;       //   lanes that must be free before new rays are handed out
-int g_opt_leaf_quorum = 16;     //   lanes holding a postponed leaf that end the node phase
-int g_opt_stream_rays = 256;    //   rays a warp takes per cursor update
+int g_opt_donate_min = 12;  // K2 on scenes with an octree filter or spheres, launches with few rounds per warp: idle lanes of a
+                           // warp take over stack entries of busy lanes once at least this many lanes are idle
+                           // (Trav::run_split); 0 = never; 100 + n = in every K1 / K2 launch (tests)
 
 int fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -310,10 +309,7 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "gpu_build")) g_opt_gpu_build = std::max(0, std::min(2, value));
   else if (!strcmp(key, "gpu_build_min_prims")) g_opt_gpu_build_min = std::max(64, value);
   else if (!strcmp(key, "render_chunks")) g_opt_chunks = std::max(1, std::min(4, value));
-  else if (!strcmp(key, "shadow_stream")) g_opt_shadow_stream = value ? 1 : 0;
-  else if (!strcmp(key, "refill_min_lanes")) g_opt_refill_min = std::max(1, std::min(32, value));
-  else if (!strcmp(key, "leaf_quorum")) g_opt_leaf_quorum = std::max(1, std::min(33, value));
-  else if (!strcmp(key, "stream_rays")) g_opt_stream_rays = std::max(32, std::min(1 << 16, value)) & ~31;
+  else if (!strcmp(key, "donate_min_lanes")) g_opt_donate_min = std::max(0, std::min(132, value));
   else if (!strcmp(key, "continue_min_lanes")) g_opt_cont_min = std::max(1, std::min(33, value));
   else return fail(RT_ERR_INVALID, "unknown option '%s'", key);
   return RT_OK;
@@ -1051,7 +1047,6 @@ const DeviceState &device_grids() {
     d.g_trace[1][1][1] = persistent_grid(k_trace_nearest<true, true, true>, 128);
     d.g_shadow[0][0] = persistent_grid(k_shadow<false, false>, 128); d.g_shadow[0][1] = persistent_grid(k_shadow<false, true>, 128);
     d.g_shadow[1][0] = persistent_grid(k_shadow<true, false>, 128); d.g_shadow[1][1] = persistent_grid(k_shadow<true, true>, 128);
-    d.g_shadow_stream[0] = persistent_grid(k_shadow_stream<false>, 128); d.g_shadow_stream[1] = persistent_grid(k_shadow_stream<true>, 128);
     d.g_frame[0][0] = persistent_grid(k_frame<false, false>, 128); d.g_frame[0][1] = persistent_grid(k_frame<false, true>, 128);
     d.g_frame[1][0] = persistent_grid(k_frame<true, false>, 128); d.g_frame[1][1] = persistent_grid(k_frame<true, true>, 128);
     d.grids_opt = g_opt_ctas_per_sm;
@@ -1084,6 +1079,7 @@ void launch_trace(RtScene *sc, bool primary, bool stats, const FrameParams *fpp,
                   FrameCounts *fc, cudaStream_t st) {
   const bool plain = scene_is_plain(sc);
   const int grid = device_grids().g_trace[primary][stats][plain];
+  sc->dev.split_min = g_opt_donate_min;
 #define RT_K1(PRIM_, STATS_, PLAIN_) k_trace_nearest<PRIM_, STATS_, PLAIN_><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, n_param, fc)
   if (primary) {
     if (stats) { if (plain) RT_K1(true, true, true); else RT_K1(true, true, false); }
@@ -1099,15 +1095,7 @@ void launch_trace(RtScene *sc, bool primary, bool stats, const FrameParams *fpp,
 void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, const LevelBufs &lv, int level, FrameCounts *fc,
                    cudaStream_t st, int *launches) {
   const bool plain = scene_is_plain(sc);
-  if (!plain && g_opt_shadow_stream) {
-    const int g = device_grids().g_shadow_stream[pl.trav_stats];
-    if (pl.trav_stats)
-      k_shadow_stream<true><<<g, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, g_opt_refill_min, g_opt_leaf_quorum, (unsigned)g_opt_stream_rays);
-    else
-      k_shadow_stream<false><<<g, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, g_opt_refill_min, g_opt_leaf_quorum, (unsigned)g_opt_stream_rays);
-    *launches += 1;
-    return;
-  }
+  sc->dev.split_min = g_opt_donate_min;
   const int grid = device_grids().g_shadow[pl.trav_stats][plain];
 #define RT_K2(STATS_, PLAIN_) k_shadow<STATS_, PLAIN_><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc)
   if (pl.trav_stats) { if (plain) RT_K2(true, true); else RT_K2(true, false); }
@@ -1389,7 +1377,7 @@ int run_pipeline(RtScene *sc, const FrameParams &fp_in, bool explicit_rays, int 
     if ((int)sc->levels.size() < pl.depth_cap + 2) sc->levels.resize(pl.depth_cap + 2);
     for (int l = 0; l <= pl.depth_cap; ++l)
       if ((rc = sc->levels[l].reserve((size_t)n0, (size_t)pl.J))) return rc;
-    const std::vector<long long> key = {g_alloc_generation.load(), n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, g_opt_graph_cond, g_opt_ctas_per_sm, g_opt_shadow_stream, g_opt_refill_min, g_opt_leaf_quorum, g_opt_stream_rays,
+    const std::vector<long long> key = {g_alloc_generation.load(), n0, pl.J, pl.Lmax, pl.S, pl.depth_cap, g_opt_graph_cond, g_opt_ctas_per_sm, g_opt_donate_min,
                                         (long long)pl.explicit_rays, (long long)pl.trav_stats};
     if (sc->graph_exec == nullptr || key != sc->graph_key) {
       if (sc->graph_exec) { cudaGraphExecDestroy(sc->graph_exec); sc->graph_exec = nullptr; }

@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
   Trav<false, STATS, PLAIN> tr;
   int stack[RT_STACK_SIZE];
   tr.idle();
+  // work donation between the lanes of a warp (Trav::run_split): pays for shadow rays of small launches (K2), not
+  // for nearest-hit rays (C3 K1 0.272 -> 0.30 ms, C5 K1 2.10 -> 2.40 ms), so it stays off here unless forced (>= 100)
+  const bool split = !PLAIN && sc.split_min >= 100;
 
   for (;;) {
     if (pool_next >= pool_end) {
@@ -176,32 +179,45 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
         if (tri_enabled || (!PLAIN && sc.n_spheres > 0)) {  // else: missed the root box, BACKGROUND
           tr.init(o, d, dest, tri_enabled, rdir);
           active = true;
+          // work donation may reuse this lane's ray registers once its own ray is done: keep the ray in the queue
+          if (PRIMARY && split) {
+            lv.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0));
+            lv.ray_d[i] = make_float4(d.x, d.y, d.z, 0.f);
+          }
         }
       }
     }
-    // ---- traverse: the whole warp, lanes without a ray idle inside run() ----
-    for (;;) {
-      tr.run(sc, st, stack, 0xffffffffu);
-      if (active && tr.finish(sc, st)) {
-        active = false;
-        fin_t = tr.best_t;
-        fin_id = tr.best_id;
+    // ---- traverse: the whole warp, lanes without a ray idle (or help, run_split) inside ----
+    if (split) {
+      tr.run_split(sc, st, stack, active, sc.split_min - 100);
+      if (active) { fin_t = tr.fin_t; fin_id = tr.fin_id; }
+    } else {
+      for (;;) {
+        tr.run(sc, st, stack, 0xffffffffu);
+        if (active && tr.finish(sc, st)) {
+          active = false;
+          fin_t = tr.best_t;
+          fin_id = tr.best_id;
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
       }
-      if (!__any_sync(0xffffffffu, active)) break;
     }
     // ---- retire (all 32 lanes converge here: one hit-list atomic per warp) ----
     const bool hit = valid && fin_id >= 0;
     const int slot = warp_append(&fc->n_hits[level], hit);
     if (valid) {
       if (hit) {
-        if (PRIMARY) {
+        V3 ro = tr.o, rd = tr.d;
+        if (split) {
+          ro = mk(lv.ray_o[i]); rd = mk(lv.ray_d[i]);
+        } else if (PRIMARY) {
           lv.ray_o[i] = make_float4(tr.o.x, tr.o.y, tr.o.z, __int_as_float(0));
           lv.ray_d[i] = make_float4(tr.d.x, tr.d.y, tr.d.z, 0.f);
         }
         lv.hit_t[i] = fin_t;
         lv.hit_face[i] = fin_id;
         lv.hit_list[slot] = i;
-        const V3 hit = add(tr.o, mul(fin_t, tr.d));  // src/flyscene.cpp:695
+        const V3 hit = add(ro, mul(fin_t, rd));  // src/flyscene.cpp:695
         lv.hit_p[slot] = make_float4(hit.x, hit.y, hit.z, __int_as_float((i << 1) | single));
       } else {
         // BACKGROUND, src/flyscene.cpp:658-665 / :684-691
@@ -302,9 +318,17 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
   Trav<true, STATS, PLAIN> tr;
   int stack[RT_STACK_SIZE];
   tr.idle();
+  // Work donation (Trav::run_split): when the launch has only a few rounds per resident warp, its run time is set by
+  // the longest rays of the last rounds (C3: 3.3 rounds per warp, SMs idle for 29 % of K2) -- idle lanes then take
+  // over pending subtrees of the lanes still traversing (K2 0.340 -> 0.28 ms).  With plenty of rounds per warp the
+  // bookkeeping costs more than the tail (C5 K2 2.17 -> 2.25 ms), so it is tied to the amount of work.
+  const int split_min = sc.split_min >= 100 ? sc.split_min - 100 : sc.split_min;
+  const bool split = !PLAIN && split_min > 0 &&
+                     (sc.split_min >= 100 || n_units < 12u * gridDim.x * (blockDim.x >> 5));
 
   for (;;) {
     bool new_job = false;
+
     if (pool_next >= pool_end) {
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(cursor, batch);
@@ -372,12 +396,19 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
         }
       }
     }
-    // ---- traverse: the whole warp, lanes without a ray idle inside run() ----
-    while (__any_sync(0xffffffffu, active)) {
-      tr.run(sc, st, stack, 0xffffffffu);
-      if (active && tr.finish(sc, st)) {
-        active = false;
-        visible = tr.occluded ? 0 : 1;
+    // ---- traverse: the whole warp, lanes without a ray idle (or help, run_split) inside ----
+    if (split) {
+      if (__any_sync(0xffffffffu, active)) {
+        tr.run_split(sc, st, stack, active, split_min);
+        if (active) visible = tr.fin_occ ? 0 : 1;
+      }
+    } else {
+      while (__any_sync(0xffffffffu, active)) {
+        tr.run(sc, st, stack, 0xffffffffu);
+        if (active && tr.finish(sc, st)) {
+          active = false;
+          visible = tr.occluded ? 0 : 1;
+        }
       }
     }
     if (slot < n_slots) {
@@ -394,133 +425,6 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
   // been traced before their gate result was visible
   if (STATS) warp_sum_add(&fc->ctr.shadow_rays_traced, traced);
   if (STATS) {
-    warp_sum_add(&fc->ctr.box_tests_k2, st.box_tests);
-    warp_sum_add(&fc->ctr.tri_tests_k2, st.tri_tests);
-    warp_sum_add(&fc->ctr.filter_checks, st.filter_checks);
-    warp_sum_add(&fc->ctr.filter_slow, st.filter_slow);
-    warp_sum_add(&fc->ctr.filter_rejects, st.filter_rejects);
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// K2, streaming form for traversal-heavy scenes: the same jobs in the same order, but a warp does not wait for the
-// longest of its 32 rays before it takes the next 32.  Any-hit rays of one tile end after very different numbers of
-// steps (profiles/r01_c3_ncu_final.txt: 11 of 32 lanes active in the node loop of k_shadow on the 1 M-triangle
-// frame), so every warp owns a run of consecutive rays (job-major order, `stream_rays` of them per cursor update)
-// and hands the next ray of that run to a lane as soon as at least `refill_min` lanes have finished theirs.
-// A ray is identified by R = unit * 32 + lane-in-unit (unit = job * n_chunks + chunk, as in k_shadow).
-// ---------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(128, 7) k_shadow_stream(const DevScene sc, const FrameParams *__restrict__ fpp,
-                                                      const LevelBufs lv, const int level, const int J, const int Lmax,
-                                                      const int S, FrameCounts *fc, const int refill_min,
-                                                      const int leaf_quorum, const unsigned stream_rays) {
-  RT_STAGE_FRAME_PARAMS(fpp);
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
-  unsigned traced = 0;
-  const unsigned n_slots = (unsigned)fc->n_hits[level];
-  const unsigned n_chunks = (n_slots + 31u) >> 5;
-  const unsigned n_rays = n_chunks * (unsigned)J * 32u;  // < 2^32 (checked by the host)
-  unsigned *cursor = reinterpret_cast<unsigned *>(&fc->work_k2[level]);
-  unsigned r_next = 0, r_end = 0;  // the warp's run of rays (warp-uniform)
-  bool exhausted = n_rays == 0u;
-
-  Trav<true, STATS, false> tr;
-  int stack[RT_STACK_SIZE];
-  tr.idle();
-  bool active = false;
-  unsigned my_slot = 0, my_j = 0;
-
-  for (;;) {
-    // ---- hand rays to the lanes that have none ----
-    const unsigned idle = __ballot_sync(0xffffffffu, !active);
-    const int n_idle = __popc(idle);
-    if (!exhausted && (n_idle >= refill_min || n_idle == 32)) {
-      if (r_next >= r_end) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(cursor, stream_rays);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_rays) exhausted = true;
-        else { r_next = base; r_end = base + stream_rays < n_rays ? base + stream_rays : n_rays; }
-      }
-      if (!exhausted) {
-        const unsigned R = r_next + (unsigned)__popc(idle & lt_mask);
-        const bool take = !active && R < r_end;
-        const unsigned left = r_end - r_next;
-        r_next += (unsigned)n_idle < left ? (unsigned)n_idle : left;
-        if (take) {
-          const unsigned unit = R >> 5;
-          const unsigned j = unit / n_chunks;
-          const unsigned slot = (unit - j * n_chunks) * 32u + (R & 31u);
-          int l = (int)j, s = -1;
-          if (j >= (unsigned)Lmax) {
-            const unsigned q = j - (unsigned)Lmax;
-            if (Lmax == 1) { l = 0; s = (int)q; }
-            else { l = (int)(q / (unsigned)S); s = (int)(q - (unsigned)l * (unsigned)S); }
-          }
-          if (slot < n_slots) {
-            const float2 hxy = *reinterpret_cast<const float2 *>(lv.hit_p + slot);
-            const V3 hit = mk(hxy.x, hxy.y, reinterpret_cast<const float *>(lv.hit_p + slot)[2]);
-            const int iw = *reinterpret_cast<volatile const int *>(reinterpret_cast<const int *>(lv.hit_p + slot) + 3);
-            V3 src;
-            bool have;
-            if (iw & 1) {
-              have = l == 0;
-              const int i = (iw & ~RT_HIT_DARK) >> 1;
-              const V3 lp = mk(lv.ray_d[i].w, lv.ray_l[i].x, lv.ray_l[i].y);
-              src = s < 0 ? lp : area_sample(fp, lp, s);
-            } else {
-              have = l < fp.n_lights;
-              src = s < 0 ? ld3(fp.lights + 3 * l)
-                          : (fp.have_sample_table ? ld3(fp.sample_table + 3 * (l * S + s)) : area_sample(fp, ld3(fp.lights + 3 * l), s));
-            }
-            if (s >= 0 && (iw & RT_HIT_DARK)) have = false;  // see k_shadow
-            uint8_t visible = 0;
-            if (have) {
-              const V3 sd = sub(hit, src);
-              const V3 rdir = recip_dir(sd);
-              traced++;
-              if (STATS) st.box_tests += 1;
-              visible = 1;
-              if (segment_reaches_bvh(sc, src, rdir, 0.98f)) {
-                const bool tri_enabled = ref_box_intersect_quick(sc.root_min, sc.root_max, src, hit, rdir);
-                if (tri_enabled || sc.n_spheres > 0) {
-                  tr.init(src, sd, hit, tri_enabled, rdir);
-                  active = true;
-                  my_slot = slot; my_j = j;
-                }
-              }
-            }
-            if (!active) lv.vis[(size_t)slot * (size_t)J + j] = visible;  // decided without a traversal (never a dark gate)
-          }
-        }
-        continue;  // lanes that got a ray needing no traversal are idle again: look once more
-      }
-    }
-    if (!__any_sync(0xffffffffu, active)) {
-      if (exhausted) break;
-      continue;
-    }
-    // ---- traverse until enough lanes are free again (to the end once no ray is left to hand out) ----
-    tr.run_stream(sc, st, stack, exhausted ? 32 : refill_min, leaf_quorum);
-    // ---- retire the finished rays ----
-    if (active && tr.traversal_done() && tr.finish(sc, st)) {
-      active = false;
-      const uint8_t visible = tr.occluded ? 0 : 1;
-      lv.vis[(size_t)my_slot * (size_t)J + my_j] = visible;
-      if (my_j == 0u && S > 0 && visible == 0) {
-        int *w = reinterpret_cast<int *>(lv.hit_p + my_slot) + 3;
-        const int iw = *reinterpret_cast<volatile int *>(w);
-        if ((iw & 1) || fp.n_lights == 1) atomicOr(w, RT_HIT_DARK);
-      }
-      tr.idle();
-    }
-  }
-  if (STATS) {
-    warp_sum_add(&fc->ctr.shadow_rays_traced, traced);
     warp_sum_add(&fc->ctr.box_tests_k2, st.box_tests);
     warp_sum_add(&fc->ctr.tri_tests_k2, st.tri_tests);
     warp_sum_add(&fc->ctr.filter_checks, st.filter_checks);

@@ -226,10 +226,11 @@ def test_c4_benchmark_config_vs_port(pkg, capi, oracle_mod):
 
 @pytest.mark.parametrize("case", ["hf224_area_d5_g4_3840x2160_s24", "hf224m_area_d5_g4_3840x2160_s48", "hf707_point_1920x1080_s20",
                                   "gallery_area_200x150", "dodge_area_rot_400x300"])
-@pytest.mark.parametrize("refill,quorum", [(8, 16), (1, 33), (24, 4)])
-def test_streaming_shadow_kernel_matches_reference_golden(case, refill, quorum, pkg, capi, scene_dir):
-    """k_shadow_stream (lane-level replacement of finished shadow rays) must decide every visibility exactly like
-    k_shadow: the goldens of the traversal-heavy scenes again, for several refill thresholds."""
+@pytest.mark.parametrize("donate_min", [101, 108, 124])
+def test_work_donation_gives_the_same_frame(case, donate_min, pkg, capi, scene_dir):
+    """Trav::run_split (idle lanes of a warp take over stack entries of busy lanes) must find every nearest hit and
+    decide every visibility exactly like the plain warp traversal: the goldens of the traversal-heavy scenes again,
+    for several donation thresholds, against the frame rendered without donation and against the reference."""
     g = load_golden(case)
     verts, fn, vn, mid, mats = scene_arrays(case, pkg, scene_dir)
     capi.init(0)
@@ -240,18 +241,20 @@ def test_streaming_shadow_kernel_matches_reference_golden(case, refill, quorum, 
     params = capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], cp["max_depth"], cp["grid"])
     try:
         capi.set_option("fused_frame", 0)
+        capi.set_option("donate_min_lanes", 0)
         ref = scene.render(cam, lights, params)
-        capi.set_option("shadow_stream", 1)
-        capi.set_option("refill_min_lanes", refill)
-        capi.set_option("leaf_quorum", quorum)
+        capi.set_option("donate_min_lanes", donate_min)
         fr = scene.render(cam, lights, params)
     finally:
-        capi.set_option("shadow_stream", 0); capi.set_option("refill_min_lanes", 8); capi.set_option("leaf_quorum", 16)
+        capi.set_option("donate_min_lanes", 12)
         capi.set_option("fused_frame", 2)
     assert (fr.rgba == ref.rgba).all() and (fr.face == ref.face).all()
+    assert (fr.t.view(np.uint32) == ref.t.view(np.uint32)).all()
     assert (fr.rgb.view(np.uint32) == ref.rgb.view(np.uint32)).all()
-    assert fr.stats["rays_shadow"] == ref.stats["rays_shadow"]
+    for k in ("rays_primary", "rays_shadow", "rays_secondary"):
+        assert fr.stats[k] == ref.stats[k]
     px, py = g["pxy"][:, 0], g["pxy"][:, 1]
+    assert (fr.face[py, px] == g["face"]).all()
     err = np.abs(fr.rgba[py, px, :3].astype(np.int64) - quant(g["rgb"])).max(-1)
     assert (err <= 1).mean() >= 0.999
     scene.close()
