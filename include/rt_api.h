@@ -165,6 +165,8 @@ int rt_device_name(char *buf, size_t n);
  *   for scenes without spheres and without an octree filter (<= 1000 triangles, e.g. the bundled cube), for frames of
  *   at most "fused_max_kpixels" thousand rays (default 1200) and for unbounded depth; other frames take the
  *   per-level wavefront kernels of csrc/rt_kernels.cuh -- both paths give bit-identical frames),
+ * "host_direct" (rt_render: when rgba_out is page-locked host memory -- cudaHostAlloc, cudaHostRegister, a pinned tensor --
+ *   the kernels store the finished pixels straight into it and no device->host copy follows; default 1),
  * "render_chunks" (rt_render of a scene that takes the fused kernel at any size: the frame is rendered in this many row
  *   chunks, 1..4, default 2, and the device->host copy of a chunk overlaps the rendering of the next),
  * "continue_min_lanes" (fused frame: child rays stay in their warp when at least this many of its lanes spawned one; default 8),

@@ -62,6 +62,12 @@ int g_opt_cont_min = 8;    // fused frame: child rays stay in the warp when at l
 int g_opt_gpu_build = 2;   // acceleration structures built on the device (rt_gpu_build.inl): 0 never, 1 whenever the scene has
                            // at least 64 primitives, 2 (default) from gpu_build_min_prims primitives on
 int g_opt_gpu_build_min = 20000;
+int g_opt_tile_w_log2 = 3;        // primary-ray tile of a warp: 2^k x (32 >> k) pixels (8 x 4)
+int g_opt_direct_tile_w_log2 = 5; // ... when the pixels go straight to a host frame: 32 x 1, one 128-byte store per warp
+int g_opt_direct_max_mb = 16;     // ... frames up to this size; larger ones are staged and copied in chunks (posted 128-byte
+                                  // writes reach ~20 GB/s, a bulk copy ~55 GB/s: C5's 133 MB frame 6.6 vs 5.3 ms end to end)
+thread_local int g_tile_override = 0;
+int g_opt_host_direct = 1; // rt_render: a page-locked host frame is written by the kernels themselves (no staging copy)
 int g_opt_chunks = 2;      // rt_render: row chunks whose device->host copy overlaps the rendering of the next chunk
 int g_opt_donate_min = 12;  // K2 on scenes with an octree filter or spheres, launches with few rounds per warp: idle lanes of a
                            // warp take over stack entries of busy lanes once at least this many lanes are idle
@@ -308,6 +314,10 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "fused_max_kpixels")) g_opt_fused_max_kpix = std::max(0, value);
   else if (!strcmp(key, "gpu_build")) g_opt_gpu_build = std::max(0, std::min(2, value));
   else if (!strcmp(key, "gpu_build_min_prims")) g_opt_gpu_build_min = std::max(64, value);
+  else if (!strcmp(key, "host_direct")) g_opt_host_direct = std::max(0, std::min(2, value));
+  else if (!strcmp(key, "host_direct_max_mb")) g_opt_direct_max_mb = std::max(0, value);
+  else if (!strcmp(key, "tile_w_log2")) g_opt_tile_w_log2 = std::max(3, std::min(5, value));
+  else if (!strcmp(key, "host_direct_tile_w_log2")) g_opt_direct_tile_w_log2 = std::max(3, std::min(5, value));
   else if (!strcmp(key, "render_chunks")) g_opt_chunks = std::max(1, std::min(4, value));
   else if (!strcmp(key, "donate_min_lanes")) g_opt_donate_min = std::max(0, std::min(132, value));
   else if (!strcmp(key, "continue_min_lanes")) g_opt_cont_min = std::max(1, std::min(33, value));
@@ -959,6 +969,7 @@ int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, con
   fp.band_rows = std::max(1, p->band_rows); fp.band_rank = p->band_rank; fp.band_world = p->band_world;
   fp.local_rows = rt_local_rows(p);
   fp.out_full_frame = p->out_full_frame ? 1 : 0;
+  fp.tile_w_log2 = g_tile_override ? g_tile_override : g_opt_tile_w_log2;
   fp.n_lights = lights->n;
   for (int i = 0; i < lights->n * 3; ++i) fp.lights[i] = lights->pos[i];
   memcpy(fp.light_color, lights->color, 12);
@@ -1521,16 +1532,38 @@ extern "C" int rt_render(RtScene *sc, const RtCamera *cam, const RtLights *light
   p = &local_p;
   // everything on the scene's own stream: frame, copies, one synchronisation at the end
   cudaStream_t st = sc->stream;
+  // A page-locked host frame (cudaHostAlloc / cudaHostRegister, e.g. a pinned tensor) is mapped into the device's
+  // address space: the kernels that finish a pixel store its uchar4 straight into it, the 8.3 MB of a 1080p frame
+  // cross PCIe as posted writes while the frame is still being rendered, and no device->host copy follows.
+  if (g_opt_host_direct && n > 0 && (g_opt_host_direct == 2 || n * 4 <= (size_t)g_opt_direct_max_mb << 20)) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, rgba_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr) {
+      g_tile_override = g_opt_direct_tile_w_log2;
+      rc = rt_render_device(sc, cam, lights, p, at.devicePointer, face_out ? sc->out_face.as<int32_t>() : nullptr,
+                            t_out ? sc->out_t.as<float>() : nullptr, rgb_f32_out ? sc->out_rgbf.as<float>() : nullptr, st, stats);
+      g_tile_override = 0;
+      if (rc) return rc;
+      if (face_out) CUDA_TRY(cudaMemcpyAsync(face_out, sc->out_face.p, n * 4, cudaMemcpyDeviceToHost, st));
+      if (t_out) CUDA_TRY(cudaMemcpyAsync(t_out, sc->out_t.p, n * 4, cudaMemcpyDeviceToHost, st));
+      if (rgb_f32_out) CUDA_TRY(cudaMemcpyAsync(rgb_f32_out, sc->out_rgbf.p, n * 12, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      return RT_OK;
+    }
+    cudaGetLastError();  // (an unregistered host pointer is reported as an error by older drivers)
+  }
   // Only the packed frame is wanted, the whole image is rendered by this call and the scene takes the fused kernel
   // at any size: render it in row chunks (one launch each) and copy chunk c to the host while chunk c+1 is being
   // rendered -- the 8.3 MB of a 1080p frame otherwise add 0.17 ms of PCIe time behind a 0.28 ms frame.
+  // (Large frames of any scene -- from 32 MB on, e.g. the 8K frame -- are chunked the same way through the wavefront
+  // kernels when the rows divide evenly, so that every chunk replays the same graph.)
+  const bool big_frame = n * 4 >= ((size_t)32 << 20) && p->height % 16 == 0;
   if (g_opt_chunks > 1 && !face_out && !t_out && !rgb_f32_out && !stats && cam && lights && p->band_world <= 1 &&
-      p->height >= 64 * g_opt_chunks && p->width > 0 && scene_is_plain(sc)) {
-    const int C = g_opt_chunks, H = p->height, W = p->width;
+      p->height >= 64 * g_opt_chunks && p->width > 0 && (scene_is_plain(sc) || big_frame)) {
+    const int C = scene_is_plain(sc) ? g_opt_chunks : 4, H = p->height, W = p->width;
     const int B = (((H + C - 1) / C) + 3) & ~3;  // rows per chunk, a multiple of the 8x4 tile height
     FrameParams probe;
     if ((rc = fill_frame(probe, cam, lights, p))) return rc;
-    if (fused_shape(probe, (long long)B * W, true, nullptr)) {
+    if (fused_shape(probe, (long long)B * W, scene_is_plain(sc), nullptr) || big_frame) {
       if (!sc->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
       for (int c = 0; c < C; ++c)
         if (!sc->ev_chunk[c]) CUDA_TRY(cudaEventCreateWithFlags(&sc->ev_chunk[c], cudaEventDisableTiming));

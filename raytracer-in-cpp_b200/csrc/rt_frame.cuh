@@ -115,14 +115,15 @@ __global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc,
   long long clk_trace = 0, clk_shadow = 0, clk_shade = 0, clk_all = 0;
   const long long clk_start = STATS ? clock64() : 0;
   int stack[RT_STACK_SIZE];
-  const int tiles_x = (fp.width + 7) >> 3;
+  const int twl = fp.tile_w_log2, tile_w = 1 << twl, tile_h = 32 >> twl;
+  const int tiles_x = (fp.width + tile_w - 1) >> twl;
   const size_t cap = (size_t)fb.n_cap;
 
   for (int phase = 0; phase <= depth_cap; ++phase) {
     // ---- work of this phase: pixel tiles (phase 0 of a camera frame) or the rays deferred to this level ----
     const bool primary = phase == 0 && !explicit0;
     unsigned int n_items;
-    if (primary) n_items = (unsigned int)tiles_x * (unsigned int)((fp.local_rows + 3) >> 2) * 32u;
+    if (primary) n_items = (unsigned int)tiles_x * (unsigned int)((fp.local_rows + tile_h - 1) / tile_h) * 32u;
     else if (phase == 0) n_items = (unsigned int)n0;
     else {
       grid_barrier(fc, phase, depth_cap);
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc,
         if (primary) {
           const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
           const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-          const int px = tx * 8 + (in_tile & 7), py = ty * 4 + (in_tile >> 3);
+          const int px = (tx << twl) + (in_tile & (tile_w - 1)), py = ty * tile_h + (in_tile >> twl);
           valid = px < fp.width && py < fp.local_rows;
           pix = py * fp.width + px;
           o = ld3(fp.eye);

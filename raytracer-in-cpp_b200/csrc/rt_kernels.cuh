@@ -109,10 +109,11 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
   float *rgb_f32 = level == 0 ? fp.out_rgbf : nullptr;
   const int lane = threadIdx.x & 31;
   TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
-  const int tiles_x = PRIMARY ? (fp.width + 7) >> 3 : 1;
+  const int twl = fp.tile_w_log2, tile_w = 1 << twl, tile_h = 32 >> twl;
+  const int tiles_x = PRIMARY ? (fp.width + tile_w - 1) >> twl : 1;
   const int n = n0 >= 0 ? n0 : fc->n_rays[level];
   const unsigned long long n_items =
-      PRIMARY ? (unsigned long long)tiles_x * (unsigned long long)((fp.local_rows + 3) >> 2) * 32ull : (unsigned long long)n;
+      PRIMARY ? (unsigned long long)tiles_x * (unsigned long long)((fp.local_rows + tile_h - 1) / tile_h) * 32ull : (unsigned long long)n;
   unsigned long long *cursor = &fc->work_k1[level];
   const unsigned long long batch = pool_batch(n_items);
   unsigned long long pool_next = 0, pool_end = 0;  // warp-local batch of work items (warp-uniform)
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
       if constexpr (PRIMARY) {
         const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int px = tx * 8 + (in_tile & 7), py = ty * 4 + (in_tile >> 3);
+        const int px = (tx << twl) + (in_tile & (tile_w - 1)), py = ty * tile_h + (in_tile >> twl);
         valid = px < fp.width && py < fp.local_rows;
         i = py * fp.width + px;
         o = ld3(fp.eye);

@@ -62,8 +62,23 @@ extern "C" int rt_render_into_frame(RtScene *sc, const RtCamera *cam, const RtLi
   if (rc) return rc;
   const size_t n = (size_t)rt_local_rows(p) * (size_t)std::max(0, p->width);
   if (n == 0) return RT_OK;
-  if ((rc = sc->out_rgba.reserve(n * 4))) return rc;
   RtParams lp = *p;
+  if (g_opt_host_direct && (g_opt_host_direct == 2 || n * 4 <= (size_t)g_opt_direct_max_mb << 20)) {
+    // a page-locked frame is mapped into this device's address space: the kernels store this rank's pixels at their
+    // global rows themselves (see rt_render), no staging buffer and no strided copy
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, rgba_full) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr) {
+      lp.out_full_frame = 1;
+      g_tile_override = g_opt_direct_tile_w_log2;
+      rc = rt_render_device(sc, cam, lights, &lp, at.devicePointer, nullptr, nullptr, nullptr, sc->stream, nullptr);
+      g_tile_override = 0;
+      if (rc) return rc;
+      CUDA_TRY(cudaStreamSynchronize(sc->stream));
+      return RT_OK;
+    }
+    cudaGetLastError();
+  }
+  if ((rc = sc->out_rgba.reserve(n * 4))) return rc;
   lp.out_full_frame = 0;
   if ((rc = rt_render_device(sc, cam, lights, &lp, sc->out_rgba.p, nullptr, nullptr, nullptr, sc->stream, nullptr))) return rc;
   if ((rc = copy_bands_into_frame(lp, sc->out_rgba.p, rgba_full, sc->stream))) return rc;

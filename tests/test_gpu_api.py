@@ -536,3 +536,35 @@ def test_chunked_render_equals_single_launch(chunks, pkg):
     finally:
         capi.set_option("render_chunks", 2)
     scene.close()
+
+
+@pytest.mark.parametrize("case", ["cube_point_1000", "hf32_point_256x144"])
+def test_page_locked_host_frame_is_written_directly(case, pkg):
+    """rt_render with a page-locked host frame: the kernels store the pixels straight into it ("host_direct", no
+    device->host copy).  Same frame, byte for byte, as through the staging copy, on the fused path (cube) and on the
+    wavefront path (height field), alone and together with the other outputs."""
+    import torch
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden(case)
+    scene = capi.Scene(g["verts"], g["fnormals"], g["vnormals"], g["mat_id"], g["mats"])
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    try:
+        for (W, H, area, point, depth) in [(640, 363, 1, 0, 3), (501, 257, 0, 1, -1)]:
+            cam = capi.default_camera(W, H)
+            params = capi.make_params(W, H, area, point, depth, (4, 4))
+            ref = scene.render(cam, lights, params)   # pageable numpy outputs: staged copies
+            pinned = torch.full((H, W, 4), 7, dtype=torch.uint8).pin_memory().numpy()
+            capi.set_option("host_direct", 1)
+            got = scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False, out_rgba=pinned)
+            assert got.rgba is pinned and (pinned == ref.rgba).all(), (case, W, H)
+            pinned[:] = 9
+            full = scene.render(cam, lights, params, out_rgba=pinned)
+            assert (pinned == ref.rgba).all() and (full.face == ref.face).all() and (full.t.view(np.uint32) == ref.t.view(np.uint32)).all()
+            capi.set_option("host_direct", 0)
+            pinned[:] = 3
+            scene.render(cam, lights, params, want_face=False, want_t=False, want_rgb=False, want_stats=False, out_rgba=pinned)
+            assert (pinned == ref.rgba).all()
+    finally:
+        capi.set_option("host_direct", 1)
+    scene.close()
