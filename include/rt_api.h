@@ -166,9 +166,13 @@ int rt_device_name(char *buf, size_t n);
  *   at most "fused_max_kpixels" thousand rays (default 1200) and for unbounded depth; other frames take the
  *   per-level wavefront kernels of csrc/rt_kernels.cuh -- both paths give bit-identical frames),
  * "host_direct" (rt_render: when rgba_out is page-locked host memory -- cudaHostAlloc, cudaHostRegister, a pinned tensor --
- *   the kernels store the finished pixels straight into it and no device->host copy follows; default 1),
- * "render_chunks" (rt_render of a scene that takes the fused kernel at any size: the frame is rendered in this many row
- *   chunks, 1..4, default 2, and the device->host copy of a chunk overlaps the rendering of the next),
+ *   the kernels store the finished pixels straight into it and no device->host copy follows; 1 = default: frames of at
+ *   most "host_direct_max_mb" MB (default 16), 2: frames of any size, 0: never; such frames are traced with
+ *   2^k x (32 >> k) pixel tiles per warp, k = "host_direct_tile_w_log2" (default 5: 32 x 1, one 128-byte store per warp);
+ *   "tile_w_log2" (default 3: 8 x 4) is the tile of every other frame),
+ * "render_chunks" (rt_render with a staged copy -- pageable or large host frames: a scene that takes the fused kernel at
+ *   any size is rendered in this many row chunks, 1..4, default 2, and the device->host copy of a chunk overlaps the
+ *   rendering of the next; frames of 32 MB and more are rendered in 4 chunks on any scene),
  * "continue_min_lanes" (fused frame: child rays stay in their warp when at least this many of its lanes spawned one; default 8),
  * "donate_min_lanes" (scenes with an octree filter or spheres, shadow kernel of launches with few rays per resident warp:
  *   lanes whose ray is finished take over pending subtrees of the lanes still traversing once at least this many lanes
