@@ -59,6 +59,10 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   *out = nullptr;
   *too_deep = false;
   const auto t_start = clk::now();
+  const bool trace_on = getenv("RT_BUILD_TRACE") != nullptr;
+  auto trace = [&](const char *what) {
+    if (trace_on) fprintf(stderr, "[rt build] %8.3f ms  %s\n", std::chrono::duration<float, std::milli>(clk::now() - t_start).count(), what);
+  };
   const int T = desc->n_faces, S = desc->n_spheres, N = T + S, M = desc->n_materials;
   if ((long long)N >= (1ll << 26)) return fail(RT_ERR_INVALID, "too many primitives (%d) for the leaf encoding", N);
   GpuBuildTimes tm;
@@ -116,6 +120,7 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
     for (int a = 0; a < 3; ++a) { vmin[a] = host_ord2f(got[a]); vmax[a] = host_ord2f(got[3 + a]); }
   }
   tm.upload_ms = ms_since(t_start);
+  trace("inputs uploaded, vertex bounds");
   float gmin[3] = {1e30f, 1e30f, 1e30f}, gmax[3] = {-1e30f, -1e30f, -1e30f};
   for (int a = 0; a < 3; ++a) {
     // BoundingBox(Mesh&): min starts at FLT_MAX, max at FLT_MIN (the smallest POSITIVE float)
@@ -242,6 +247,7 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
     }
   }
   tm.octree_ms = ms_since(t_oct);
+  trace("octree");
   sc->octree_ms = tm.octree_ms;
 
   // ---- 2. primitive boxes, Morton order ----
@@ -270,6 +276,7 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   }
   const int32_t *sorted_ids = ids.Current();
   tm.sort_ms = ms_since(t_sort);
+  trace("boxes, Morton sort (queued)");
 
   // ---- 3. BVH: binned SAH splits, one launch pair (big nodes / small nodes) per tree level ----
   const auto t_bvh = clk::now();
@@ -324,6 +331,7 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
     }
   }
   tm.bvh_ms = ms_since(t_bvh);
+  trace("BVH levels");
 
   // ---- 4. pair nodes ----
   const auto t_emit = clk::now();
@@ -336,7 +344,9 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   CUDA_TRY(cudaMemcpy(&last_pos, ppos + n_nodes_tree - 1, 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(&last_flag, pflag + n_nodes_tree - 1, 4, cudaMemcpyDeviceToHost));
   const int n_pairs_out = last_pos + last_flag;
+  trace("pair flags scanned");
   if ((rc = sc->nodes.reserve((size_t)std::max(n_pairs_out, 1) * 64))) return rc;
+  trace("nodes allocated");
   RT_ARENA(d_leaves, perm, unsigned, 4);
   RT_ARENA(d_depth, perm, int32_t, 4);
   RT_ARENA(d_sah, perm, double, 2);
@@ -350,7 +360,9 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
   if (tree_depth > RT_STACK_SIZE - 3) { *too_deep = true; return RT_OK; }  // (cannot happen: the builder guards its depth)
 
   // ---- 5. bake ----
+  trace("pairs emitted (depth read back)");
   if ((rc = sc->prims.reserve((size_t)N * 80)) || (rc = sc->shade.reserve((size_t)std::max(T, 1) * 112))) return rc;
+  trace("soup + shading table allocated");
   k_bake_prims<<<cdiv((size_t)N, 256), 256>>>(N, T, prim_order, d_verts, d_fn, d_mat, d_illum, sc->spheres.as<float>(),
                                              sc->sphere_mat.as<int32_t>(), sc->prims.as<float4>());
   if (T > 0) k_bake_shade<<<cdiv((size_t)T, 256), 256>>>(T, d_verts, d_fn, d_vn, d_mat, sc->shade.as<float4>());
@@ -367,6 +379,7 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
     root_area = std::max(1e-30, dx * dy + dy * dz + dz * dx);
   }
   CUDA_TRY(cudaGetLastError());
+  trace("baked, results read back");
   memcpy(dv.bvh_min, rb, 12);
   memcpy(dv.bvh_max, rb + 3, 12);
   dv.n_nodes = n_pairs_out;
@@ -386,6 +399,7 @@ int gpu_build_scene(const RtSceneDesc *desc, RtScene **out, bool *too_deep) {
       cudaMallocHost((void **)&sc->h_fcounts, sizeof(FusedCounts)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(RT_ERR_CUDA, "cudaMallocHost failed");
+  trace("workspace (pinned counters, stream)");
   tm.total_ms = ms_since(t_start);
   sc->build_ms = tm.total_ms;
   sc->build_phase_ms[0] = tm.upload_ms; sc->build_phase_ms[1] = tm.octree_ms; sc->build_phase_ms[2] = tm.sort_ms;
