@@ -63,7 +63,7 @@ int g_opt_gpu_build = 2;   // acceleration structures built on the device (rt_gp
                            // at least 64 primitives, 2 (default) from gpu_build_min_prims primitives on
 int g_opt_gpu_build_min = 20000;
 int g_opt_tile_w_log2 = 3;        // primary-ray tile of a warp: 2^k x (32 >> k) pixels (8 x 4)
-int g_opt_direct_tile_w_log2 = 5; // ... when the pixels go straight to a host frame: 32 x 1, one 128-byte store per warp
+int g_opt_direct_tile_w_log2 = 4; // ... when the pixels go straight to a host frame: 16 x 2, two 64-byte stores per warp
 int g_opt_direct_max_mb = 16;     // ... frames up to this size; larger ones are staged and copied in chunks (posted 128-byte
                                   // writes reach ~20 GB/s, a bulk copy ~55 GB/s: C5's 133 MB frame 6.6 vs 5.3 ms end to end)
 thread_local int g_tile_override = 0;

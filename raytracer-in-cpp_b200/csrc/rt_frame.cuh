@@ -36,8 +36,18 @@
 
 namespace rtd {
 
+#ifndef RT_SHADE_UNROLL
+#define RT_SHADE_UNROLL 2
+#endif
+// Resident CTAs per SM the frame kernel is compiled for (register budget 65536 / (128 * MINB)).  The PLAIN
+// instantiation (the bundled scenes) runs best with 7 CTAs = 72 registers: its stalls are fixed-latency dependencies
+// (`wait`), which a seventh warp per scheduler hides -- C2 0.272 -> 0.254 ms; 8 CTAs (64 registers) spill too much
+// (0.257 ms), 5 CTAs 0.293 ms (A/B of builds on one box, tools/ab_gpu.sh).
 #ifndef RT_FRAME_MINB
-#define RT_FRAME_MINB 6  // resident CTAs per SM the frame kernel is compiled for (register budget 65536 / (128 * MINB))
+#define RT_FRAME_MINB 6
+#endif
+#ifndef RT_FRAME_MINB_PLAIN
+#define RT_FRAME_MINB_PLAIN 7
 #endif
 #define RT_FUSED_MAX_LEVELS 9   // levels 0..8: max_depth <= 8 (deeper caps take the wavefront path)
 #define RT_FUSED_MAX_JOBS 64    // shadow jobs per hit held as a bit mask
@@ -106,7 +116,7 @@ __device__ __forceinline__ V3 fold_chain(const FusedBufs &fb, int parent, V3 c) 
 }
 
 template <bool STATS, bool PLAIN>
-__global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc, const FrameParams fp, const FusedBufs fb,
+__global__ void __launch_bounds__(128, PLAIN ? RT_FRAME_MINB_PLAIN : RT_FRAME_MINB) k_frame(const DevScene sc, const FrameParams fp, const FusedBufs fb,
                                                   FusedCounts *fc, const int n0, const int explicit0, const int J,
                                                   const int Lmax, const int S, const int depth_cap, const int cont_min) {
   const int lane = threadIdx.x & 31;
@@ -299,7 +309,29 @@ __global__ void __launch_bounds__(128, RT_FRAME_MINB) k_frame(const DevScene sc,
               float sum = 0.f;
               V3 acc = mk(0.f, 0.f, 0.f);
               const V3 lpos = single ? lp : ld3(fp.lights + 3 * l);
+#if RT_SHADE_UNROLL > 1
+              // RT_SHADE_UNROLL samples per iteration: their (independent) normalisation / pow chains overlap in
+              // the pipeline; the sums are taken in sample order, so the result is that of the one-by-one loop
+              // (C1 0.119 -> 0.115 ms, C2 +-0; 4 at a time: C2 +3 %)
+              int s = 0;
+              for (; s + RT_SHADE_UNROLL <= ns; s += RT_SHADE_UNROLL) {
+                const int bit = Lmax + l * S + s;  // (ns > 1 only in area mode)
+                const unsigned vbits = (unsigned)(vis >> bit) & ((1u << RT_SHADE_UNROLL) - 1u);
+                if (vbits == 0u) continue;
+                V3 ph[RT_SHADE_UNROLL];
+#pragma unroll
+                for (int u = 0; u < RT_SHADE_UNROLL; ++u) {
+                  const V3 sp = (!single && fp.have_sample_table) ? ld3(fp.sample_table + 3 * (l * S + s + u)) : area_sample(fp, lpos, s + u);
+                  ph[u] = phong_sample(Ikd, Iks, m.ns, P, sp, normal, eye);
+                }
+#pragma unroll
+                for (int u = 0; u < RT_SHADE_UNROLL; ++u)
+                  if ((vbits >> u) & 1u) { sum += 1.f; acc = add(acc, ph[u]); samples_shaded++; }
+              }
+              for (; s < ns; ++s) {
+#else
               for (int s = 0; s < ns; ++s) {
+#endif
                 const int bit = fp.point_light ? l : Lmax + l * S + s;
                 if (!((vis >> bit) & 1ull)) continue;
                 sum += 1.f;
