@@ -135,7 +135,7 @@ struct DevBuf {
 };
 
 struct LevelStore {
-  DevBuf ray_o, ray_d, ray_l, hit_t, hit_face, hit_list, hit_p, vis, rec, child, type;
+  DevBuf ray_o, ray_d, ray_l, hit_t, hit_face, hit_list, hit_p, lit_list, vis, rec, child, type;
   int reserve(size_t n, size_t J) {
     n = std::max<size_t>(n, 1);
     int rc;
@@ -146,6 +146,7 @@ struct LevelStore {
     if ((rc = hit_face.reserve(n * 4))) return rc;
     if ((rc = hit_list.reserve(n * 4))) return rc;
     if ((rc = hit_p.reserve(n * 16))) return rc;
+    if ((rc = lit_list.reserve(n * 4))) return rc;
     if ((rc = vis.reserve(n * std::max<size_t>(J, 1)))) return rc;
     if ((rc = rec.reserve(n * 16))) return rc;
     if ((rc = child.reserve(n * 4))) return rc;
@@ -157,12 +158,13 @@ struct LevelStore {
     b.ray_o = ray_o.as<float4>(); b.ray_d = ray_d.as<float4>(); b.ray_l = ray_l.as<float2>();
     b.hit_t = hit_t.as<float>(); b.hit_face = hit_face.as<int32_t>(); b.hit_list = hit_list.as<int32_t>();
     b.hit_p = hit_p.as<float4>();
+    b.lit_list = lit_list.as<int32_t>();
     b.vis = vis.as<uint8_t>();
     b.rec = rec.as<float4>(); b.child = child.as<int32_t>(); b.type = type.as<uint8_t>();
     return b;
   }
   void release() {
-    ray_o.release(); ray_d.release(); ray_l.release(); hit_t.release(); hit_face.release(); hit_list.release(); hit_p.release();
+    ray_o.release(); ray_d.release(); ray_l.release(); hit_t.release(); hit_face.release(); hit_list.release(); hit_p.release(); lit_list.release();
     vis.release(); rec.release(); child.release(); type.release();
   }
 };
@@ -1108,11 +1110,14 @@ void launch_shadow(RtScene *sc, const FramePlan &pl, const FrameParams *fpp, con
   const bool plain = scene_is_plain(sc);
   sc->dev.split_min = g_opt_donate_min;
   const int grid = device_grids().g_shadow[pl.trav_stats][plain];
-#define RT_K2(STATS_, PLAIN_) k_shadow<STATS_, PLAIN_><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc)
-  if (pl.trav_stats) { if (plain) RT_K2(true, true); else RT_K2(true, false); }
-  else { if (plain) RT_K2(false, true); else RT_K2(false, false); }
+#define RT_K2(STATS_, PLAIN_, PASS_) k_shadow<STATS_, PLAIN_><<<grid, 128, 0, st>>>(sc->dev, fpp, lv, level, pl.J, pl.Lmax, pl.S, fc, PASS_)
+  // area mode: gate rays first, then the sample rays of the hits whose gate passed (compacted: full warps)
+  for (int pass = pl.S > 0 ? 1 : 0; pass <= (pl.S > 0 ? 2 : 0); ++pass) {
+    if (pl.trav_stats) { if (plain) RT_K2(true, true, pass); else RT_K2(true, false, pass); }
+    else { if (plain) RT_K2(false, true, pass); else RT_K2(false, false, pass); }
+    *launches += 1;
+  }
 #undef RT_K2
-  *launches += 1;
 }
 
 // enqueue the launches of levels [0, depth_cap] and the folds (async mode: all of them)

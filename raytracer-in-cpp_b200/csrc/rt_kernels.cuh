@@ -19,7 +19,6 @@
 namespace rtd {
 
 // record types written by K3 and consumed by K3b
-#define RT_HIT_DARK 0x40000000  // hit_p.w flag: the hit's only light is occluded, its sample rays are moot
 
 enum RecType : uint8_t {
   REC_TERMINAL = 0,        // rec.xyz is the final colour of this ray
@@ -39,6 +38,7 @@ struct LevelBufs {
   int32_t *hit_face;  // -1: no hit
   int32_t *hit_list;  // compacted indices of the rays that hit something (K1 -> K2, K3)
   float4 *hit_p;      // per hit slot: (hit point, bits((ray index << 1) | single-light flag)) (K1 -> K2)
+  int32_t *lit_list;  // area mode: hit slots whose gate passed, i.e. the hits that shoot sample rays (K2 pass 1 -> pass 2)
   uint8_t *vis;       // [hit slot][J] visibility of every shadow job
   float4 *rec;        // (P or colour, fresnel factor)
   int32_t *child;     // slot of the child ray in the next level, -1 if none
@@ -64,6 +64,7 @@ struct FrameCounts {
   unsigned long long work_k2[RT_MAX_LEVELS];
   int32_t n_rays[RT_MAX_LEVELS];              // rays queued at level k (k >= 1; level 0 comes as a parameter)
   int32_t n_hits[RT_MAX_LEVELS];              // rays of level k that hit a primitive
+  int32_t n_lit[RT_MAX_LEVELS];               // ... of which the gate passed (area mode; K2 pass 1)
   uint32_t k3_done[RT_MAX_LEVELS];            // CTAs of K3(level k) that have finished (last one sets the graph condition)
   Counters ctr;
 };
@@ -296,20 +297,30 @@ __device__ __forceinline__ V3 light_sample(const FrameParams &fp, const RayLight
 // surface patch, far more coherent than the S rays that fan out from one hit point; and at any moment
 // all warps of the GPU work on the same one or two samples, which keeps the upper tree levels of that
 // bundle in L1.  j is warp-uniform, the per-job set-up is one 16-byte load of the hit point (hit_p).
+//
+// Area mode runs in two launches.  The reference shoots no sample rays for a hit whose gate failed (SHADOW,
+// src/flyscene.cpp:699-710: it returns before phongShade), and on a frame with real shadows a third of the hits are
+// dark (C4: 31 %) -- as lanes of the sample units they would idle for the whole unit (ncu on C4: 22.8 of 32 lanes
+// held a ray when a unit started).  So pass 1 (`pass` = 1) traces the gate jobs and appends the slots of the hits
+// that go on to phongShade to lit_list (ballot + popc, one atomic per warp), and pass 2 traces the sample jobs over
+// 32 consecutive entries of that list: full warps again.  Point mode (S = 0) has gate jobs only: one launch, pass 0.
 // ---------------------------------------------------------------------------------------------
 template <bool STATS, bool PLAIN>
 __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const FrameParams *__restrict__ fpp,
                                                const LevelBufs lv, const int level, const int J, const int Lmax,
-                                               const int S, FrameCounts *fc) {
+                                               const int S, FrameCounts *fc, const int pass) {
   RT_STAGE_FRAME_PARAMS(fpp);
   const int lane = threadIdx.x & 31;
   TravStats st; st.box_tests = 0; st.tri_tests = 0; st.filter_checks = 0; st.filter_slow = 0; st.filter_rejects = 0;
   unsigned traced = 0;
-  const unsigned n_slots = (unsigned)fc->n_hits[level];
+  const unsigned n_slots = pass == 2 ? (unsigned)fc->n_lit[level] : (unsigned)fc->n_hits[level];
   const unsigned n_chunks = (n_slots + 31u) >> 5;
-  const unsigned n_units = n_chunks * (unsigned)J;  // < 2^27: the host refuses frames with n0 * J >= 2^32
-  // (32-bit cursor in the low word of the 64-bit counter: a warp overshoots n_units by at most one batch)
-  unsigned *cursor = reinterpret_cast<unsigned *>(&fc->work_k2[level]);
+  const unsigned j_first = pass == 2 ? (unsigned)Lmax : 0u;                          // jobs of this pass
+  const unsigned j_count = pass == 0 ? (unsigned)J : (pass == 1 ? (unsigned)Lmax : (unsigned)(J - Lmax));
+  const unsigned n_units = n_chunks * j_count;  // < 2^27: the host refuses frames with n0 * J >= 2^32
+  // (32-bit cursors in the two words of the 64-bit counter -- pass 2 takes the high one --: a warp overshoots
+  // n_units by at most one batch)
+  unsigned *cursor = reinterpret_cast<unsigned *>(&fc->work_k2[level]) + (pass == 2 ? 1 : 0);
   const unsigned batch = (unsigned)(pool_batch((unsigned long long)n_units * 32ull) >> 5);  // units per cursor update
   unsigned pool_next = 0, pool_end = 0;  // warp-local batch of units (warp-uniform)
   // job and chunk of the current unit, advanced incrementally (one division per batch, not per unit)
@@ -337,15 +348,18 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
       if (base >= n_units) break;
       pool_next = base;
       pool_end = base + batch < n_units ? base + batch : n_units;
-      j = base / n_chunks;
-      chunk = base - j * n_chunks;
+      const unsigned jj = base / n_chunks;
+      j = j_first + jj;
+      chunk = base - jj * n_chunks;
       new_job = true;
     } else if (++chunk == n_chunks) {
       chunk = 0; ++j;
       new_job = true;
     }
     pool_next += 1u;
-    const unsigned slot = chunk * 32u + (unsigned)lane;
+    const unsigned entry = chunk * 32u + (unsigned)lane;  // position in hit_list order (pass 0, 1) or in lit_list (pass 2)
+    const bool in_range = entry < n_slots;
+    const unsigned slot = !in_range ? 0u : (pass == 2 ? (unsigned)lv.lit_list[entry] : entry);
     if (new_job) {
       l = (int)j; s = -1;
       if (j >= (unsigned)Lmax) {
@@ -356,17 +370,16 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
     }
     bool active = false, have = false;
     uint8_t visible = 0;
-    if (slot < n_slots) {
-      const float2 hxy = *reinterpret_cast<const float2 *>(lv.hit_p + slot);
-      const V3 hit = mk(hxy.x, hxy.y, reinterpret_cast<const float *>(lv.hit_p + slot)[2]);
-      // the flag word may be set concurrently by the gate unit of this hit (atomicOr below): read it with a
-      // relaxed volatile load of its own instead of as part of the float4
-      const int iw = *reinterpret_cast<volatile const int *>(reinterpret_cast<const int *>(lv.hit_p + slot) + 3);
+    int iw = 0;
+    if (in_range) {
+      const float4 hp = lv.hit_p[slot];
+      const V3 hit = mk(hp);
+      iw = __float_as_int(hp.w);
       V3 src;
       if (iw & 1) {
         // mirror child: its light list is the single point it inherited (the parent's hit point)
         have = l == 0;
-        const int i = (iw & ~RT_HIT_DARK) >> 1;
+        const int i = iw >> 1;
         const V3 lp = mk(lv.ray_d[i].w, lv.ray_l[i].x, lv.ray_l[i].y);
         src = s < 0 ? lp : area_sample(fp, lp, s);
       } else {
@@ -374,12 +387,6 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
         src = s < 0 ? ld3(fp.lights + 3 * l)
                     : (fp.have_sample_table ? ld3(fp.sample_table + 3 * (l * S + s)) : area_sample(fp, ld3(fp.lights + 3 * l), s));
       }
-      // Sample rays of a hit whose gate failed are never looked at (SHADOW, src/flyscene.cpp:699-710: the
-      // reference returns before phongShade).  For hits with a single light the gate unit leaves a flag
-      // in hit_p.w (below); gate units precede all sample units in the unit order, so a sample unit
-      // almost always sees it and skips the ray.  Seeing a stale copy only costs a ray nobody uses: the
-      // frame does not depend on the timing.
-      if (s >= 0 && (iw & RT_HIT_DARK)) have = false;
       if (have) {
         const V3 sd = sub(hit, src);  // :920
         const V3 rdir = recip_dir(sd);
@@ -412,14 +419,14 @@ __global__ void __launch_bounds__(128, 7) k_shadow(const DevScene sc, const Fram
         }
       }
     }
-    if (slot < n_slots) {
-      lv.vis[(size_t)slot * (size_t)J + j] = visible;
-      if (j == 0u && S > 0 && visible == 0) {
-        // gate ray of light 0 occluded: if it is the hit's only light, flag the hit
-        int *w = reinterpret_cast<int *>(lv.hit_p + slot) + 3;
-        const int iw = *reinterpret_cast<volatile int *>(w);
-        if ((iw & 1) || fp.n_lights == 1) atomicOr(w, RT_HIT_DARK);
-      }
+    if (in_range) lv.vis[(size_t)slot * (size_t)J + j] = visible;
+    if (pass == 1 && j == 0u) {
+      // The hit goes on to phongShade unless its gate failed.  With one light (the scene's only one, or the single
+      // inherited point of a mirror child) that is this ray's verdict; with several lights every hit stays in the
+      // list (its other gates are other units) and K3 applies the gate.
+      const bool lit = in_range && !(((iw & 1) || fp.n_lights == 1) && visible == 0);
+      const int pos = warp_append(&fc->n_lit[level], lit);
+      if (lit) lv.lit_list[pos] = (int32_t)slot;
     }
   }
   // rays actually traced (work; the census is counted by K3): a few sample rays of dark hits may have
