@@ -168,8 +168,11 @@ int rt_device_name(char *buf, size_t n);
  * "host_direct" (rt_render: when rgba_out is page-locked host memory -- cudaHostAlloc, cudaHostRegister, a pinned tensor --
  *   the kernels store the finished pixels straight into it and no device->host copy follows; 1 = default: frames of at
  *   most "host_direct_max_mb" MB (default 16), 2: frames of any size, 0: never; such frames are traced with
- *   2^k x (32 >> k) pixel tiles per warp, k = "host_direct_tile_w_log2" (default 4: 16 x 2, two 64-byte stores per warp; 5 = 32 x 1);
+ *   2^k x (32 >> k) pixel tiles per warp, k = "host_direct_tile_w_log2" (default 5: 32 x 1, one 128-byte store per warp);
  *   "tile_w_log2" (default 3: 8 x 4) is the tile of every other frame),
+ * "tile_order" (1 = default: the pixel tiles inside the screen rectangle of the scene's bounds are handed out first, so
+ *   that a launch ends on cheap background tiles -- except for frames written straight to a host frame, whose pixel
+ *   stores must stay spread over the frame time; 0 = row-major order; 2 = always first),
  * "render_chunks" (rt_render with a staged copy -- pageable or large host frames: a scene that takes the fused kernel at
  *   any size is rendered in this many row chunks, 1..4, default 2, and the device->host copy of a chunk overlaps the
  *   rendering of the next; frames of 32 MB and more are rendered in 4 chunks on any scene),

@@ -63,10 +63,12 @@ int g_opt_gpu_build = 2;   // acceleration structures built on the device (rt_gp
                            // at least 64 primitives, 2 (default) from gpu_build_min_prims primitives on
 int g_opt_gpu_build_min = 20000;
 int g_opt_tile_w_log2 = 3;        // primary-ray tile of a warp: 2^k x (32 >> k) pixels (8 x 4)
-int g_opt_direct_tile_w_log2 = 4; // ... when the pixels go straight to a host frame: 16 x 2, two 64-byte stores per warp
+int g_opt_direct_tile_w_log2 = 5; // ... when the pixels go straight to a host frame: 32 x 1, one 128-byte store per warp
 int g_opt_direct_max_mb = 16;     // ... frames up to this size; larger ones are staged and copied in chunks (posted 128-byte
                                   // writes reach ~20 GB/s, a bulk copy ~55 GB/s: C5's 133 MB frame 6.6 vs 5.3 ms end to end)
 thread_local int g_tile_override = 0;
+int g_opt_tile_order = 1;  // pixel tiles that can see the scene's bounds are handed out first, except when the pixels go
+                           // straight to a host frame (set_tile_rect); 0 = row-major, 2 = always first
 int g_opt_host_direct = 1; // rt_render: a page-locked host frame is written by the kernels themselves (no staging copy)
 int g_opt_chunks = 2;      // rt_render: row chunks whose device->host copy overlaps the rendering of the next chunk
 int g_opt_donate_min = 12;  // K2 on scenes with an octree filter or spheres, launches with few rounds per warp: idle lanes of a
@@ -318,6 +320,7 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "gpu_build_min_prims")) g_opt_gpu_build_min = std::max(64, value);
   else if (!strcmp(key, "host_direct")) g_opt_host_direct = std::max(0, std::min(2, value));
   else if (!strcmp(key, "host_direct_max_mb")) g_opt_direct_max_mb = std::max(0, value);
+  else if (!strcmp(key, "tile_order")) g_opt_tile_order = std::max(0, std::min(2, value));
   else if (!strcmp(key, "tile_w_log2")) g_opt_tile_w_log2 = std::max(3, std::min(5, value));
   else if (!strcmp(key, "host_direct_tile_w_log2")) g_opt_direct_tile_w_log2 = std::max(3, std::min(5, value));
   else if (!strcmp(key, "render_chunks")) g_opt_chunks = std::max(1, std::min(4, value));
@@ -946,6 +949,54 @@ void sphere_offsets(uint32_t seed, float radius, float *out /*[25][3]*/) {
   }
 }
 
+// Screen rectangle (in tiles of the frame's tile shape) of the scene's bounds: its tiles are handed out first
+// (tile_xy in rt_device.cuh).  Only an ordering hint: a wrong or empty rectangle cannot change a pixel.
+void set_tile_rect(FrameParams &fp, const RtScene *sc) {
+  fp.tile_rect[0] = fp.tile_rect[1] = fp.tile_rect[2] = fp.tile_rect[3] = 0;
+  // (pixels stored straight into a host frame -- rt_render's direct path sets the tile override -- keep row-major order)
+  if (!g_opt_tile_order || sc->dev.n_prims <= 0 || (g_tile_override != 0 && g_opt_tile_order == 1)) return;
+  const int tw = 1 << fp.tile_w_log2, th = 32 >> fp.tile_w_log2;
+  const int tiles_x = (fp.width + tw - 1) / tw, tiles_y = (fp.local_rows + th - 1) / th;
+  // camera space of the bounds' corners: view_inv = [R | t] maps camera to world
+  const float *m = fp.view_inv;
+  const double R[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]}, t[3] = {m[3], m[7], m[11]};
+  const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+  if (!(std::fabs(det) > 1e-20)) return;
+  const double Ri[9] = {(R[4] * R[8] - R[5] * R[7]) / det, (R[2] * R[7] - R[1] * R[8]) / det, (R[1] * R[5] - R[2] * R[4]) / det,
+                        (R[5] * R[6] - R[3] * R[8]) / det, (R[0] * R[8] - R[2] * R[6]) / det, (R[2] * R[3] - R[0] * R[5]) / det,
+                        (R[3] * R[7] - R[4] * R[6]) / det, (R[1] * R[6] - R[0] * R[7]) / det, (R[0] * R[4] - R[1] * R[3]) / det};
+  auto to_cam = [&](const double w[3], double c[3]) {
+    const double d[3] = {w[0] - t[0], w[1] - t[1], w[2] - t[2]};
+    for (int a = 0; a < 3; ++a) c[a] = Ri[3 * a] * d[0] + Ri[3 * a + 1] * d[1] + Ri[3 * a + 2] * d[2];
+  };
+  const double eye_w[3] = {fp.eye[0], fp.eye[1], fp.eye[2]};
+  double e[3];
+  to_cam(eye_w, e);
+  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+  for (int corner = 0; corner < 8; ++corner) {
+    const double w[3] = {(corner & 1) ? sc->dev.bvh_max[0] : sc->dev.bvh_min[0], (corner & 2) ? sc->dev.bvh_max[1] : sc->dev.bvh_min[1],
+                         (corner & 4) ? sc->dev.bvh_max[2] : sc->dev.bvh_min[2]};
+    if (!std::isfinite(w[0]) || !std::isfinite(w[1]) || !std::isfinite(w[2])) return;
+    double c[3];
+    to_cam(w, c);
+    const double dz = c[2] - e[2];
+    if (!(dz < -1e-9)) return;  // a corner beside or behind the eye: no bounded rectangle
+    const double sdist = (-1.0 - e[2]) / dz;  // the screen is the plane z = -1 of camera space (screenToWorld)
+    if (!(sdist > 0.0)) return;
+    const double sx = e[0] + sdist * (c[0] - e[0]), sy = e[1] + sdist * (c[1] - e[1]);
+    const double px = (sx / fp.cam_sx + 1.0) * 0.5 * fp.viewport[2] + fp.viewport[0];
+    const double py = (1.0 - sy / fp.cam_sy) * 0.5 * fp.viewport[3] + fp.viewport[1];
+    xmin = std::min(xmin, px); xmax = std::max(xmax, px); ymin = std::min(ymin, py); ymax = std::max(ymax, py);
+  }
+  if (!(xmin <= xmax) || !(ymin <= ymax)) return;
+  auto clampi = [](double v, int lo, int hi) { return (int)std::max((double)lo, std::min((double)hi, v)); };
+  int x0 = clampi(std::floor(xmin / tw) - 1, 0, tiles_x), x1 = clampi(std::floor(xmax / tw) + 2, 0, tiles_x);
+  int y0 = clampi(std::floor(ymin / th) - 1, 0, tiles_y), y1 = clampi(std::floor(ymax / th) + 2, 0, tiles_y);
+  if (fp.band_world > 1) { y0 = 0; y1 = tiles_y; }  // interleaved bands: local rows are not global rows; order by column only
+  if (x1 <= x0 || y1 <= y0 || (x0 == 0 && y0 == 0 && x1 == tiles_x && y1 == tiles_y)) return;
+  fp.tile_rect[0] = x0; fp.tile_rect[1] = y0; fp.tile_rect[2] = x1; fp.tile_rect[3] = y1;
+}
+
 int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, const RtParams *p) {
   memset(&fp, 0, sizeof(fp));
   if (!lights || !p) return fail(RT_ERR_INVALID, "null lights/params");
@@ -1516,6 +1567,7 @@ extern "C" int rt_render_device(RtScene *sc, const RtCamera *cam, const RtLights
   if (rc) return rc;
   FrameParams fp;
   if ((rc = fill_frame(fp, cam, lights, p))) return rc;
+  set_tile_rect(fp, sc);
   const long long n0 = (long long)fp.local_rows * fp.width;
   if (n0 > 0x7fffffffLL / 32) return fail(RT_ERR_LIMIT, "image too large for one call (%lld pixels); shard it in bands", n0);
   if (n0 == 0) return RT_OK;

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(128, PLAIN ? RT_FRAME_MINB_PLAIN : RT_FRAME_MI
       if (item < pool_end) {
         if (primary) {
           const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
-          const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+          int tx, ty;
+          tile_xy(fp, tile, tiles_x, (fp.local_rows + tile_h - 1) / tile_h, tx, ty);
           const int px = (tx << twl) + (in_tile & (tile_w - 1)), py = ty * tile_h + (in_tile >> twl);
           valid = px < fp.width && py < fp.local_rows;
           pix = py * fp.width + px;

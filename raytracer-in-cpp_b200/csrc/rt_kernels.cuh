@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
       bool tri_enabled = true;
       if constexpr (PRIMARY) {
         const int tile = (int)(item >> 5), in_tile = (int)(item & 31);
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        int tx, ty;
+        tile_xy(fp, tile, tiles_x, (fp.local_rows + tile_h - 1) / tile_h, tx, ty);
         const int px = (tx << twl) + (in_tile & (tile_w - 1)), py = ty * tile_h + (in_tile >> twl);
         valid = px < fp.width && py < fp.local_rows;
         i = py * fp.width + px;

@@ -568,3 +568,37 @@ def test_page_locked_host_frame_is_written_directly(case, pkg):
     finally:
         capi.set_option("host_direct", 1)
     scene.close()
+
+
+@pytest.mark.parametrize("case", ["cube_rot_500x400", "dodge_area_rot_400x300", "hf32_point_256x144"])
+def test_tile_order_does_not_change_the_frame(case, pkg, scene_dir):
+    """Pixel tiles inside the screen rectangle of the scene's bounds are handed out first ("tile_order"): only the
+    order of the work changes.  Same frame with and without, for rotated cameras, both frame paths, every tile shape
+    and a band-sharded share."""
+    from conftest import case_params, scene_arrays
+    capi = pkg.capi
+    capi.init(0)
+    g = load_golden(case)
+    verts, fn, vn, mid, mats = scene_arrays(case, pkg, scene_dir)
+    scene = capi.Scene(verts, fn, vn, mid, mats, g["model_matrix"])
+    cp = case_params(g)
+    cam = capi.make_camera(g["eye"], g["view_inv"], g["viewport"], float(g["cam"][0]), float(g["cam"][1]))
+    lights = capi.Lights(g["lights"], g["light_color"])
+    try:
+        for fused in (0, 1):
+            capi.set_option("fused_frame", fused)
+            for twl in (3, 4, 5):
+                capi.set_option("tile_w_log2", twl)
+                for world in (1, 3):
+                    params = capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], cp["max_depth"], cp["grid"],
+                                              8 if world > 1 else 0, 1 if world > 1 else 0, world)
+                    capi.set_option("tile_order", 0)
+                    a = scene.render(cam, lights, params)
+                    for order in (1, 2):  # the scene's rectangle first (2: also for direct host frames)
+                        capi.set_option("tile_order", order)
+                        b = scene.render(cam, lights, params)
+                        assert (a.rgba == b.rgba).all() and (a.face == b.face).all(), (fused, twl, world, order)
+                        assert (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
+    finally:
+        capi.set_option("tile_order", 1); capi.set_option("tile_w_log2", 3); capi.set_option("fused_frame", 2)
+    scene.close()
