@@ -132,11 +132,13 @@ typedef struct {
   int64_t box_tests_shadow, tri_tests_shadow;
   /* reference-candidate filter: winners checked, checks that needed the exact octree walk, rejections */
   int64_t filter_checks, filter_slow, filter_rejects;
-  /* any-hit queries the shadow kernel actually traced ("stats" option): it skips the sample rays of a hit
-   * once that hit's gate result is known to be "no light visible", and may trace a few before it is */
+  /* any-hit queries the shadow kernels actually traced ("stats" option): equal to rays_shadow -- the sample rays of a
+   * hit whose gate failed are neither asked for by the reference nor traced here */
   int64_t shadow_rays_traced;
-  /* 1: the frame ran as ONE persistent kernel (csrc/rt_frame.cuh); ms_trace / ms_shadow / ms_shade are then that
-   * kernel's duration split by the warp-cycles its phases took ("stats" option), not separate launches */
+  /* which frame path ran: 0 = wavefront kernels replayed as one CUDA graph (depth caps 0..8), 1 = ONE persistent kernel
+   * (csrc/rt_frame.cuh; ms_trace / ms_shadow / ms_shade are then that kernel's duration split by the warp-cycles its
+   * phases took ("stats" option), not separate launches), 2 = wavefront kernels launched level by level with a host
+   * read-back of the next level's ray count after each (unbounded depth, or a depth cap above 8) */
   int32_t fused;
 } RtStats;
 
