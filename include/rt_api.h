@@ -175,6 +175,8 @@ int rt_device_name(char *buf, size_t n);
  * "tile_order" (1 = default: the pixel tiles inside the screen rectangle of the scene's bounds are handed out first, so
  *   that a launch ends on cheap background tiles -- except for frames written straight to a host frame, whose pixel
  *   stores must stay spread over the frame time; 0 = row-major order; 2 = always first),
+ * "tile_cull" (1 = default: pixel tiles outside that rectangle -- widened by one tile -- cannot see the scene: their
+ *   pixels are BACKGROUND without a ray being generated; 0 = every pixel runs the reference's two root-box tests),
  * "render_chunks" (rt_render with a staged copy -- pageable or large host frames: a scene that takes the fused kernel at
  *   any size is rendered in this many row chunks, 1..4, default 2, and the device->host copy of a chunk overlaps the
  *   rendering of the next; frames of 32 MB and more are rendered in 4 chunks on any scene),

@@ -68,6 +68,7 @@ int g_opt_direct_tile_w_log2 = 5; // ... when the pixels go straight to a host f
 int g_opt_direct_max_mb = 16;     // ... frames up to this size; larger ones are staged and copied in chunks (posted 128-byte
                                   // writes reach ~20 GB/s, a bulk copy ~55 GB/s: C5's 133 MB frame 6.6 vs 5.3 ms end to end)
 thread_local int g_tile_override = 0;
+int g_opt_tile_cull = 1;   // pixel tiles that cannot see the scene's bounds are background without tracing (tile_outside)
 int g_opt_tile_order = 1;  // pixel tiles that can see the scene's bounds are handed out first, except when the pixels go
                            // straight to a host frame (set_tile_rect); 0 = row-major, 2 = always first
 int g_opt_host_direct = 1; // rt_render: a page-locked host frame is written by the kernels themselves (no staging copy)
@@ -321,6 +322,7 @@ extern "C" int rt_set_option(const char *key, int value) {
   else if (!strcmp(key, "gpu_build_min_prims")) g_opt_gpu_build_min = std::max(64, value);
   else if (!strcmp(key, "host_direct")) g_opt_host_direct = std::max(0, std::min(2, value));
   else if (!strcmp(key, "host_direct_max_mb")) g_opt_direct_max_mb = std::max(0, value);
+  else if (!strcmp(key, "tile_cull")) g_opt_tile_cull = value ? 1 : 0;
   else if (!strcmp(key, "tile_order")) g_opt_tile_order = std::max(0, std::min(2, value));
   else if (!strcmp(key, "tile_w_log2")) g_opt_tile_w_log2 = std::max(3, std::min(5, value));
   else if (!strcmp(key, "host_direct_tile_w_log2")) g_opt_direct_tile_w_log2 = std::max(3, std::min(5, value));
@@ -960,8 +962,8 @@ void sphere_offsets(uint32_t seed, float radius, float *out /*[25][3]*/) {
 // (tile_xy in rt_device.cuh).  Only an ordering hint: a wrong or empty rectangle cannot change a pixel.
 void set_tile_rect(FrameParams &fp, const RtScene *sc) {
   fp.tile_rect[0] = fp.tile_rect[1] = fp.tile_rect[2] = fp.tile_rect[3] = 0;
-  // (pixels stored straight into a host frame -- rt_render's direct path sets the tile override -- keep row-major order)
-  if (!g_opt_tile_order || sc->dev.n_prims <= 0 || (g_tile_override != 0 && g_opt_tile_order == 1)) return;
+  fp.tile_order_on = 0; fp.tile_cull = 0;
+  if ((!g_opt_tile_order && !g_opt_tile_cull) || sc->dev.n_prims <= 0) return;
   const int tw = 1 << fp.tile_w_log2, th = 32 >> fp.tile_w_log2;
   const int tiles_x = (fp.width + tw - 1) / tw, tiles_y = (fp.local_rows + th - 1) / th;
   // camera space of the bounds' corners: view_inv = [R | t] maps camera to world
@@ -1002,6 +1004,9 @@ void set_tile_rect(FrameParams &fp, const RtScene *sc) {
   if (fp.band_world > 1) { y0 = 0; y1 = tiles_y; }  // interleaved bands: local rows are not global rows; order by column only
   if (x1 <= x0 || y1 <= y0 || (x0 == 0 && y0 == 0 && x1 == tiles_x && y1 == tiles_y)) return;
   fp.tile_rect[0] = x0; fp.tile_rect[1] = y0; fp.tile_rect[2] = x1; fp.tile_rect[3] = y1;
+  // (pixels stored straight into a host frame -- rt_render's direct path sets the tile override -- keep row-major order)
+  fp.tile_order_on = (g_opt_tile_order == 2 || (g_opt_tile_order == 1 && g_tile_override == 0)) ? 1 : 0;
+  fp.tile_cull = g_opt_tile_cull ? 1 : 0;
 }
 
 int fill_frame(FrameParams &fp, const RtCamera *cam, const RtLights *lights, const RtParams *p) {

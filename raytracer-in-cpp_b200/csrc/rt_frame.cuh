@@ -172,6 +172,15 @@ __global__ void __launch_bounds__(128, PLAIN ? RT_FRAME_MINB_PLAIN : RT_FRAME_MI
           valid = px < fp.width && py < fp.local_rows;
           pix = py * fp.width + px;
           o = ld3(fp.eye);
+          if (tile_outside(fp, tx, ty)) {  // (warp-uniform) the whole tile is BACKGROUND, src/flyscene.cpp:658-665
+            if (valid) {
+              if (fp.out_face) fp.out_face[pix] = -1;
+              if (fp.out_t) fp.out_t[pix] = RT_NO_HIT_T;
+              if (fp.out_rgba) fp.out_rgba[fb_index(fp, pix)] = make_uchar4(255, 255, 255, 255);
+              if (fp.out_rgbf) { fp.out_rgbf[3 * (size_t)pix] = 1.f; fp.out_rgbf[3 * (size_t)pix + 1] = 1.f; fp.out_rgbf[3 * (size_t)pix + 2] = 1.f; }
+            }
+            continue;
+          }
           if (valid) {
             screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
             d = sub(screen, o);  // :619, not normalised

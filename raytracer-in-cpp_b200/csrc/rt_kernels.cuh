@@ -155,6 +155,17 @@ __global__ void __launch_bounds__(128, 7) k_trace_nearest(const DevScene sc, con
         i = py * fp.width + px;
         o = ld3(fp.eye);
         d = mk(0.f, 0.f, 0.f);
+        if (tile_outside(fp, tx, ty)) {  // (warp-uniform) the whole tile is BACKGROUND, src/flyscene.cpp:658-665
+          if (valid) {
+            lv.rec[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            lv.type[i] = (uint8_t)REC_TERMINAL;
+            if (fb) fb[fb_index(fp, i)] = make_uchar4(255, 255, 255, 255);
+            if (rgb_f32) { rgb_f32[3 * (size_t)i] = 1.f; rgb_f32[3 * (size_t)i + 1] = 1.f; rgb_f32[3 * (size_t)i + 2] = 1.f; }
+            if (face_out) face_out[i] = -1;
+            if (t_out) t_out[i] = RT_NO_HIT_T;
+          }
+          continue;
+        }
         if (valid) {
           screen = screen_to_world(fp, (float)px, (float)global_row(fp, py));
           d = sub(screen, o);  // :619, not normalised

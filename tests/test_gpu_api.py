@@ -592,13 +592,17 @@ def test_tile_order_does_not_change_the_frame(case, pkg, scene_dir):
                 for world in (1, 3):
                     params = capi.make_params(cp["w"], cp["h"], cp["area"], cp["point"], cp["max_depth"], cp["grid"],
                                               8 if world > 1 else 0, 1 if world > 1 else 0, world)
-                    capi.set_option("tile_order", 0)
+                    capi.set_option("tile_order", 0); capi.set_option("tile_cull", 0)
                     a = scene.render(cam, lights, params)
+                    capi.set_option("tile_cull", 1)  # tiles outside the scene's screen rectangle: background untraced
+                    c = scene.render(cam, lights, params)
+                    assert (a.rgba == c.rgba).all() and (a.face == c.face).all() and (a.t.view(np.uint32) == c.t.view(np.uint32)).all()
+                    assert (a.rgb.view(np.uint32) == c.rgb.view(np.uint32)).all()
                     for order in (1, 2):  # the scene's rectangle first (2: also for direct host frames)
                         capi.set_option("tile_order", order)
                         b = scene.render(cam, lights, params)
                         assert (a.rgba == b.rgba).all() and (a.face == b.face).all(), (fused, twl, world, order)
                         assert (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
     finally:
-        capi.set_option("tile_order", 1); capi.set_option("tile_w_log2", 3); capi.set_option("fused_frame", 2)
+        capi.set_option("tile_order", 1); capi.set_option("tile_cull", 1); capi.set_option("tile_w_log2", 3); capi.set_option("fused_frame", 2)
     scene.close()
