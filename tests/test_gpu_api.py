@@ -606,3 +606,50 @@ def test_tile_order_does_not_change_the_frame(case, pkg, scene_dir):
     finally:
         capi.set_option("tile_order", 1); capi.set_option("tile_cull", 1); capi.set_option("tile_w_log2", 3); capi.set_option("fused_frame", 2)
     scene.close()
+
+
+def test_tile_cull_with_unusual_cameras(pkg, scene_dir):
+    """The tile rectangle must stay conservative (or switch itself off) for cameras the goldens do not cover: far away
+    (the scene is a few tiles), close up (the scene is larger than the screen), eye inside the scene's bounds, scene
+    behind the eye, rotated and sheared view matrices, an eye that is not the view matrix' translation, an offset
+    viewport, a very wide field of view.  Frames with and without culling must be identical in every output."""
+    from conftest import scene_arrays
+    capi = pkg.capi
+    capi.init(0)
+    verts, fn, vn, mid, mats = scene_arrays("hf32_point_256x144", pkg, scene_dir)
+    scene = capi.Scene(verts, fn, vn, mid, mats)
+    lights = capi.Lights(np.array([[-1, 1, 1]], np.float32))
+    W, H = 322, 187
+
+    def rot(ax, ay):
+        cx, sx, cy, sy = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay)
+        return np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+
+    cams = []
+    for eye, R, fovy, vp, eye_off in [
+            ((0, 0, 12), np.eye(3), 60.0, (0, 0, W, H), 0),          # far away
+            ((0, 0.1, 0.6), np.eye(3), 60.0, (0, 0, W, H), 0),       # close up
+            ((0, 0.0, 0.0), np.eye(3), 60.0, (0, 0, W, H), 0),       # inside the bounds
+            ((0, 0, -3), np.eye(3), 60.0, (0, 0, W, H), 0),          # scene behind the eye
+            ((1.5, 1.0, 2.0), rot(-0.4, 0.6), 45.0, (0, 0, W, H), 0),  # rotated
+            ((0.3, 0.2, 2.5), rot(0.2, -0.3) @ np.array([[1, 0.2, 0], [0, 1, 0], [0, 0, 1.0]]), 70.0, (0, 0, W, H), 0),  # sheared
+            ((0, 0, 2.0), np.eye(3), 60.0, (0, 0, W, H), 1),         # eye differs from the matrix' translation
+            ((0, 0, 2.5), np.eye(3), 60.0, (13, -7, W + 40, H + 25), 0),  # offset / larger viewport
+            ((0, 0, 1.2), rot(0.1, 0.0), 150.0, (0, 0, W, H), 0)]:   # very wide
+        t = np.asarray(eye, np.float64) + (np.array([0.3, -0.2, 0.1]) if eye_off else 0)
+        vi = np.concatenate([R, t.reshape(3, 1)], 1).astype(np.float32)
+        cams.append(capi.make_camera(eye, vi, vp, fovy, np.float32(W) / np.float32(H)))
+    try:
+        for k, cam in enumerate(cams):
+            for fused in (0, 1):
+                capi.set_option("fused_frame", fused)
+                params = capi.make_params(W, H, 0, 1, 1, (5, 5))
+                capi.set_option("tile_cull", 0); capi.set_option("tile_order", 0)
+                a = scene.render(cam, lights, params)
+                capi.set_option("tile_cull", 1); capi.set_option("tile_order", 1)
+                b = scene.render(cam, lights, params)
+                assert (a.rgba == b.rgba).all() and (a.face == b.face).all(), (k, fused)
+                assert (a.t.view(np.uint32) == b.t.view(np.uint32)).all() and (a.rgb.view(np.uint32) == b.rgb.view(np.uint32)).all()
+    finally:
+        capi.set_option("tile_cull", 1); capi.set_option("tile_order", 1); capi.set_option("fused_frame", 2)
+    scene.close()
