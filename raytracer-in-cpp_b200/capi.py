@@ -552,7 +552,7 @@ class HostFrame:
 
 
 class Multi:
-    """One host process, N GPUs (rt_multi_*): scene baked once, uploaded to every device."""
+    """One host process, N GPUs (rt_multi_*): large scenes are built by every device itself, all at once; small ones are baked once on the host and uploaded."""
 
     def __init__(self, devices, verts, fnormals, vnormals, mat_id, mats, model_matrix=None, spheres=None, sphere_mat=None):
         d = Scene._make_desc(self, verts, fnormals, vnormals, mat_id, mats, model_matrix, spheres, sphere_mat)
