@@ -7,6 +7,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
+#include <chrono>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace rt {
 
@@ -24,6 +31,33 @@ bool read_file(const std::string &path, std::string &out) {
   out.resize(got);
   return true;
 }
+
+// the OBJ text, memory-mapped (read into a buffer when it cannot be mapped)
+struct TextFile {
+  const char *data = nullptr;
+  size_t size = 0;
+  void *mapped = nullptr;
+  std::string fallback;
+  bool open(const std::string &path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd >= 0) {
+      struct stat st;
+      if (::fstat(fd, &st) == 0 && st.st_size > 0) {
+        void *p = ::mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p != MAP_FAILED) {
+          ::madvise(p, (size_t)st.st_size, MADV_SEQUENTIAL);
+          mapped = p; data = (const char *)p; size = (size_t)st.st_size;
+        }
+      }
+      ::close(fd);
+      if (mapped) return true;
+    }
+    if (!read_file(path, fallback)) return false;
+    data = fallback.data(); size = fallback.size();
+    return true;
+  }
+  ~TextFile() { if (mapped) ::munmap(mapped, size); }
+};
 
 std::string dir_of(const std::string &p) {
   size_t k = p.find_last_of("/\\");
@@ -109,39 +143,40 @@ bool load_mtl(const std::string &path, std::vector<RtMaterial> &out, std::vector
   return true;
 }
 
-BakedMesh load_obj(const std::string &obj_path, bool normalize) {
-  std::string buf;
-  if (!read_file(obj_path, buf)) throw std::runtime_error("Cannot open " + obj_path);
-  const std::string base = dir_of(obj_path);
+namespace {
 
-  BakedMesh m;
-  std::vector<float> file_vn;                       // vn lines, in file order
-  std::vector<std::vector<uint32_t>> groups(1);     // flat vertex-id lists, one per usemtl run
-  std::vector<int> group_mat(1, -1);
-  int current_mat = -1;
+// What one thread found in its slice of the OBJ text (whole lines).  A face id counted back from "the vertices read
+// so far" (a negative id) needs the number of vertices in the slices before this one: it is stored relative to the
+// slice's first vertex, its position noted in `relative`, and the merge adds the slice's vertex offset.
+struct ObjSlice {
+  std::vector<float> v, vn;
+  std::vector<int64_t> ids;        // zero-based vertex id of every face corner, in file order
+  std::vector<size_t> relative;    // positions in ids that hold slice-relative values
+  struct Event { size_t at; int kind; std::string name; };  // kind 0: mtllib, 1: usemtl; `at` = position in ids
+  std::vector<Event> events;
+  std::string error;
+};
 
-  LineReader lr(buf);
-  const char *b, *e;
-  while (lr.next(b, e)) {
+void parse_slice(const char *p, const char *end, ObjSlice &out, const std::string &obj_path) {
+  while (p < end) {
+    const char *b = p;
+    const char *nl = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+    const char *e = nl ? nl : end;
+    p = nl ? nl + 1 : end;
     if (starts(b, e, "mtllib")) {
       std::string fn(b + std::min<ptrdiff_t>(7, e - b), e);
       fn.erase(std::remove(fn.begin(), fn.end(), '\r'), fn.end());
-      load_mtl(base + fn, m.materials, m.material_names);
-      if (m.materials.empty()) { m.materials.push_back(default_material()); m.material_names.emplace_back(); }
+      out.events.push_back({out.ids.size(), 0, std::move(fn)});
     } else if (starts(b, e, "usemtl")) {
-      if (!groups.back().empty()) { groups.emplace_back(); group_mat.push_back(-1); }
-      std::string name(b + std::min<ptrdiff_t>(7, e - b), e);
-      for (size_t i = 0; i < m.material_names.size(); ++i)
-        if (m.material_names[i] == name) current_mat = (int)i;
-      group_mat.back() = current_mat;
+      out.events.push_back({out.ids.size(), 1, std::string(b + std::min<ptrdiff_t>(7, e - b), e)});
     } else if (starts(b, e, "v ")) {
       float v[3];
       parse3(b + 2, v);
-      m.obj_verts.insert(m.obj_verts.end(), v, v + 3);
+      out.v.insert(out.v.end(), v, v + 3);
     } else if (starts(b, e, "vn")) {
       float v[3] = {0, 0, 0};
       if (e - b > 3) parse3(b + 3, v);
-      file_vn.insert(file_vn.end(), v, v + 3);
+      out.vn.insert(out.vn.end(), v, v + 3);
     } else if (starts(b, e, "f ")) {
       // "f v[/vt[/vn]] ..." -- only the vertex id of each element is used by the ray tracer
       const char *c = b + 2;
@@ -154,36 +189,163 @@ BakedMesh load_obj(const std::string &obj_path, bool normalize) {
         // OBJ ids are 1-based; a negative id counts back from the vertices read so far.  Anything that does
         // not name an existing vertex would index past obj_verts / normals below: reject the file instead
         // (the reference reads out of bounds there, tucano/utils/objimporter.hpp:196-214).
-        const long nv_here = (long)(m.obj_verts.size() / 3);
-        const long zero_based = id < 0 ? nv_here + id : id - 1;
-        if (id == 0 || zero_based < 0) throw std::runtime_error("face index " + std::to_string(id) + " out of range in " + obj_path);
-        groups.back().push_back((uint32_t)zero_based);
+        if (id == 0) {
+          if (out.error.empty()) out.error = "face index 0 out of range in " + obj_path;
+          return;
+        }
+        if (id < 0) {
+          out.relative.push_back(out.ids.size());
+          out.ids.push_back((int64_t)id + (int64_t)(out.v.size() / 3));
+        } else {
+          out.ids.push_back((int64_t)id - 1);
+        }
         c = q;
         while (c < e && *c != ' ' && *c != '\t' && *c != '\r') ++c;  // skip /vt/vn
       }
     }
   }
+}
+
+// f(k) for k in [0, n) on up to `threads` host threads (strided: neighbouring k cost about the same)
+template <class F>
+void parallel_for(size_t n, unsigned threads, F f) {
+  threads = (unsigned)std::min<size_t>(std::max(1u, threads), std::max<size_t>(n, 1));
+  if (threads <= 1) {
+    for (size_t k = 0; k < n; ++k) f(k);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([=] { for (size_t k = t; k < n; k += threads) f(k); });
+  for (auto &th : pool) th.join();
+}
+// f(begin, end) over contiguous blocks of [0, n)
+template <class F>
+void parallel_blocks(size_t n, unsigned threads, F f) {
+  threads = (unsigned)std::min<size_t>(std::max(1u, threads), std::max<size_t>(n / 4096, 1));
+  const size_t step = (n + threads - 1) / std::max(1u, threads);
+  parallel_for(threads, threads, [=](size_t t) { f(std::min(n, t * step), std::min(n, (t + 1) * step)); });
+}
+
+}  // namespace
+
+// The OBJ text is cut into slices at line ends and parsed by all host cores (number parsing is most of the load time
+// of a large file), the slices are merged in file order, and the per-face work -- edge normalisations, face normals,
+// the baked arrays -- runs in parallel over faces.  Every float sum whose order the reference fixes (a vertex' normal
+// over its faces in file order, the centroid over the vertices) is still taken in that order.
+BakedMesh load_obj(const std::string &obj_path, bool normalize) {
+  const auto t_start = std::chrono::high_resolution_clock::now();
+  const bool trace = std::getenv("RT_LOAD_TRACE") != nullptr;
+  auto lap = [&](const char *what) {
+    if (trace) std::fprintf(stderr, "[rt load] %8.3f ms  %s\n", std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t_start).count(), what);
+  };
+  TextFile buf;
+  if (!buf.open(obj_path)) throw std::runtime_error("Cannot open " + obj_path);
+  lap("file mapped");
+  const std::string base = dir_of(obj_path);
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const unsigned n_slices = buf.size < (1u << 20) ? 1u : hw;
+
+  // ---- parse ----
+  std::vector<ObjSlice> slices(n_slices);
+  {
+    std::vector<size_t> cut(n_slices + 1, buf.size);
+    cut[0] = 0;
+    for (unsigned k = 1; k < n_slices; ++k) {
+      const size_t at = std::max(cut[k - 1], buf.size / n_slices * k);
+      const void *nl = at < buf.size ? std::memchr(buf.data + at, '\n', buf.size - at) : nullptr;
+      cut[k] = nl ? (size_t)((const char *)nl - buf.data) + 1 : buf.size;
+    }
+    parallel_for(n_slices, n_slices,
+                 [&](size_t k) { parse_slice(buf.data + cut[k], buf.data + cut[k + 1], slices[k], obj_path); });
+  }
+
+  lap("parsed");
+  // ---- merge in file order: vertices, vn's, face ids (negative ids resolved), usemtl runs ----
+  BakedMesh m;
+  std::vector<float> file_vn;                // vn lines, in file order
+  std::vector<uint32_t> ids;                 // vertex ids of all face corners, in file order
+  std::vector<size_t> group_begin(1, 0);     // a group = the face corners between two usemtl lines
+  std::vector<int> group_mat(1, -1);
+  int current_mat = -1;
+  {
+    size_t nv = 0, nvn = 0, nid = 0;
+    for (const auto &sl : slices) { nv += sl.v.size(); nvn += sl.vn.size(); nid += sl.ids.size(); }
+    m.obj_verts.reserve(nv); file_vn.reserve(nvn); ids.reserve(nid);
+  }
+  for (auto &sl : slices) {
+    if (!sl.error.empty()) throw std::runtime_error(sl.error);
+    const int64_t v_base = (int64_t)(m.obj_verts.size() / 3);
+    for (size_t pos : sl.relative) {
+      sl.ids[pos] += v_base;
+      if (sl.ids[pos] < 0) throw std::runtime_error("relative face index reaches before the first vertex in " + obj_path);
+    }
+    size_t done = 0;
+    auto copy_ids = [&](size_t upto) {
+      for (; done < upto; ++done) {
+        if (sl.ids[done] > 0xfffffffell) throw std::runtime_error("face index too large in " + obj_path);
+        ids.push_back((uint32_t)sl.ids[done]);
+      }
+    };
+    for (const auto &e : sl.events) {
+      copy_ids(e.at);
+      if (e.kind == 0) {
+        load_mtl(base + e.name, m.materials, m.material_names);
+        if (m.materials.empty()) { m.materials.push_back(default_material()); m.material_names.emplace_back(); }
+      } else {
+        if (ids.size() > group_begin.back()) { group_begin.push_back(ids.size()); group_mat.push_back(-1); }
+        for (size_t k = 0; k < m.material_names.size(); ++k)
+          if (m.material_names[k] == e.name) current_mat = (int)k;
+        group_mat.back() = current_mat;
+      }
+    }
+    copy_ids(sl.ids.size());
+    m.obj_verts.insert(m.obj_verts.end(), sl.v.begin(), sl.v.end());
+    file_vn.insert(file_vn.end(), sl.vn.begin(), sl.vn.end());
+    ObjSlice().v.swap(sl.v);
+  }
+  group_begin.push_back(ids.size());
   const size_t NV = m.obj_verts.size() / 3;
-  for (const auto &g : groups)
-    for (uint32_t id : g)
-      if ((size_t)id >= NV)
-        throw std::runtime_error("face index " + std::to_string((unsigned long)id + 1) + " exceeds the " + std::to_string(NV) +
-                                 " vertices of " + obj_path);
+  for (uint32_t id : ids)
+    if ((size_t)id >= NV)
+      throw std::runtime_error("face index " + std::to_string((unsigned long)id + 1) + " exceeds the " + std::to_string(NV) +
+                               " vertices of " + obj_path);
   auto V = [&](uint32_t i) { return Vec3f(&m.obj_verts[3 * (size_t)i]); };
+  lap("merged");
+
+  // ---- faces: corner triples inside each group (a group's one or two left-over corners are dropped) ----
+  std::vector<size_t> face_corner;           // position in ids of every face's first corner
+  std::vector<int32_t> face_mat;
+  for (size_t g = 0; g + 1 < group_begin.size(); ++g)
+    for (size_t i = group_begin[g]; i + 2 < group_begin[g + 1]; i += 3) {
+      face_corner.push_back(i);
+      // OBJ files without mtllib/usemtl give material -1 in the reference (UB there); map to 0
+      face_mat.push_back(group_mat[g] < 0 ? 0 : group_mat[g]);
+    }
+  const size_t T = face_corner.size();
 
   // ---- vertex normals: list = file vn's followed by NV zero vectors; face normals are
   // accumulated at the *vertex* index, then everything is normalised (objimporter.hpp:50-74) ----
   std::vector<Vec3f> normals(file_vn.size() / 3 + NV);
   for (size_t i = 0; i < file_vn.size() / 3; ++i) normals[i] = Vec3f(&file_vn[3 * i]);
-  for (const auto &g : groups)
-    for (size_t i = 0; i + 2 < g.size(); i += 3) {
-      Vec3f v1 = normalized(V(g[i + 2]) - V(g[i]));
-      Vec3f v0 = normalized(V(g[i + 1]) - V(g[i]));
-      Vec3f n = normalized(cross(v0, v1));
-      normals[g[i]] += n; normals[g[i + 1]] += n; normals[g[i + 2]] += n;
+  {
+    std::vector<Vec3f> acc_n(T);
+    parallel_blocks(T, hw, [&](size_t lo, size_t hi) {
+      for (size_t f = lo; f < hi; ++f) {
+        const uint32_t *g = &ids[face_corner[f]];
+        const Vec3f v1 = normalized(V(g[2]) - V(g[0]));
+        const Vec3f v0 = normalized(V(g[1]) - V(g[0]));
+        acc_n[f] = normalized(cross(v0, v1));
+      }
+    });
+    for (size_t f = 0; f < T; ++f) {  // (in file order: float sums are not associative)
+      const uint32_t *g = &ids[face_corner[f]];
+      normals[g[0]] += acc_n[f]; normals[g[1]] += acc_n[f]; normals[g[2]] += acc_n[f];
     }
-  for (auto &n : normals) n = normalized(n);
+  }
+  parallel_blocks(normals.size(), hw, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) normals[i] = normalized(normals[i]); });
 
+  lap("vertex normals");
   // ---- centroid / bounding-sphere radius / normalisation (mesh.hpp:621-642) ----
   Vec3f c(0, 0, 0);
   for (size_t i = 0; i < NV; ++i) c = c + V((uint32_t)i);
@@ -201,35 +363,35 @@ BakedMesh load_obj(const std::string &obj_path, bool normalize) {
     return Vec3f(s * p.x + tr.x, s * p.y + tr.y, s * p.z + tr.z);
   };
 
+  lap("centroid, radius");
   // ---- faces, in group order (mesh.hpp:441-468) ----
-  size_t T = 0;
-  for (const auto &g : groups) T += g.size() / 3;
-  m.verts.reserve(T * 9); m.fnormals.reserve(T * 3); m.vnormals.reserve(T * 9);
-  m.mat_id.reserve(T); m.vertex_ids.reserve(T * 3);
+  m.verts.resize(T * 9); m.fnormals.resize(T * 3); m.vnormals.resize(T * 9);
+  m.mat_id.resize(T); m.vertex_ids.resize(T * 3);
   if (m.materials.empty()) { m.materials.push_back(default_material()); m.material_names.emplace_back(); }
-  for (size_t gi = 0; gi < groups.size(); ++gi) {
-    const auto &g = groups[gi];
-    for (size_t i = 0; i + 2 < g.size(); i += 3) {
-      const uint32_t ids[3] = {g[i], g[i + 1], g[i + 2]};
+  parallel_blocks(T, hw, [&](size_t lo, size_t hi) {
+    for (size_t f = lo; f < hi; ++f) {
+      const uint32_t *g = &ids[face_corner[f]];
       for (int k = 0; k < 3; ++k) {
-        Vec3f w = W(ids[k]);
-        m.verts.insert(m.verts.end(), w.data(), w.data() + 3);
-        const Vec3f &n = normals[ids[k]];
-        m.vnormals.insert(m.vnormals.end(), n.data(), n.data() + 3);
-        m.vertex_ids.push_back((int32_t)ids[k]);
+        const Vec3f w = W(g[k]);
+        const Vec3f &n = normals[g[k]];
+        for (int a = 0; a < 3; ++a) {
+          m.verts[9 * f + 3 * k + a] = w[a];
+          m.vnormals[9 * f + 3 * k + a] = n[a];
+        }
+        m.vertex_ids[3 * f + k] = (int32_t)g[k];
       }
       // face normal from *object-space* normalised edges.  The reference normalises these two
       // edges through a dynamic-size Eigen expression (Vector4f::head(3) differences), whose
       // squared norm is reduced left to right, (x*x + y*y) + z*z -- unlike every fixed-size
       // 3-vector elsewhere (mesh.hpp:461-462 vs Redux.h); the cross product is fixed-size again.
-      Vec3f e1 = normalized_ltr(V(ids[2]) - V(ids[0]));
-      Vec3f e0 = normalized_ltr(V(ids[1]) - V(ids[0]));
-      Vec3f fn = normalized(cross(e0, e1));
-      m.fnormals.insert(m.fnormals.end(), fn.data(), fn.data() + 3);
-      // OBJ files without mtllib/usemtl give material -1 in the reference (UB there); map to 0
-      m.mat_id.push_back(group_mat[gi] < 0 ? 0 : group_mat[gi]);
+      const Vec3f e1 = normalized_ltr(V(g[2]) - V(g[0]));
+      const Vec3f e0 = normalized_ltr(V(g[1]) - V(g[0]));
+      const Vec3f fn = normalized(cross(e0, e1));
+      for (int a = 0; a < 3; ++a) m.fnormals[3 * f + a] = fn[a];
+      m.mat_id[f] = face_mat[f];
     }
-  }
+  });
+  lap("baked");
   return m;
 }
 

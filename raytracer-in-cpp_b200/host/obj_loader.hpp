@@ -7,12 +7,15 @@
 //   vertex normals   objimporter.hpp:50-74 (accumulated by vertex id on top of the file's vn list)
 //   normalisation    mesh.hpp:621-642, model.hpp:169-173 (scale 1/radius about the centroid)
 //   material params  materials/mtl.hpp:16-116
-// All citations relative to /root/reference.  This is a fresh implementation (single pass over a
-// memory-mapped buffer, no iostreams in the vertex/face loops), not a copy of those files.
+// All citations relative to /root/reference.  This is a fresh implementation (the memory-mapped text is parsed in slices by all
+// host cores, no iostreams in the vertex/face loops), not a copy of those files.
 #pragma once
 
 #include <cstdint>
+#include <memory>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/rt_api.h"
@@ -20,13 +23,24 @@
 
 namespace rt {
 
+// std::vector whose resize() leaves new elements uninitialised: the loader sizes the per-face arrays once and fills
+// them from all host cores; value-initialising ~100 MB first would touch every page from one thread.
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+  template <class U> struct rebind { using other = default_init_allocator<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U *p) { ::new (static_cast<void *>(p)) U; }
+  template <class U, class... Args> void construct(U *p, Args &&...args) { ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...); }
+};
+template <class T> using RawVector = std::vector<T, default_init_allocator<T>>;
+
 struct BakedMesh {
   // per face (T entries)
-  std::vector<float> verts;      // [T][3][3] world space
-  std::vector<float> fnormals;   // [T][3]
-  std::vector<float> vnormals;   // [T][3][3]
-  std::vector<int32_t> mat_id;   // [T]
-  std::vector<int32_t> vertex_ids;  // [T][3]
+  RawVector<float> verts;      // [T][3][3] world space
+  RawVector<float> fnormals;   // [T][3]
+  RawVector<float> vnormals;   // [T][3][3]
+  RawVector<int32_t> mat_id;   // [T]
+  RawVector<int32_t> vertex_ids;  // [T][3]
   std::vector<RtMaterial> materials;
   std::vector<std::string> material_names;
   // object-space data
