@@ -243,8 +243,12 @@ BakedMesh load_obj(const std::string &obj_path, bool normalize) {
   if (!buf.open(obj_path)) throw std::runtime_error("Cannot open " + obj_path);
   lap("file mapped");
   const std::string base = dir_of(obj_path);
-  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  const unsigned n_slices = buf.size < (1u << 20) ? 1u : hw;
+  unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  unsigned n_slices = buf.size < (1u << 20) ? 1u : hw;
+  if (const char *forced = std::getenv("RT_LOAD_THREADS")) {  // (tests: any slice count, also on small files)
+    const int n = std::atoi(forced);
+    if (n >= 1 && n <= 64) { hw = (unsigned)n; n_slices = (unsigned)std::min<size_t>((size_t)n, std::max<size_t>(buf.size / 64, 1)); }
+  }
 
   // ---- parse ----
   std::vector<ObjSlice> slices(n_slices);

@@ -298,3 +298,53 @@ def test_adaptive_band_height_partitions_every_frame(pkg):
                 sizes = [len(x) for x in rows]
                 assert max(sizes) - min(sizes) <= B
                 assert 4 <= -(-H // B) // world <= 9  # about 8 bands per rank
+
+
+def test_loader_slices_parse_like_one_pass(pkg, tmp_path, monkeypatch):
+    """The OBJ text is parsed in slices by several host threads and merged in file order.  Whatever the number of
+    slices -- cuts fall between any two lines -- the bake is the one-pass bake, bit for bit: interleaved v / vn / f
+    lines, several usemtl runs, face ids counted back from the vertices read so far (resolved against the vertex
+    offset of their slice), vt/vn suffixes, blank and comment lines, CRLF."""
+    capi = pkg.capi
+    rng = np.random.default_rng(3)
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 1 0 0\nnewmtl b\nKd 0 1 0\nillum 4\nnewmtl c\nKd 0 0 1\n")
+    lines = ["mtllib m.mtl", "# generated"]
+    nv = 0
+    for block in range(60):
+        lines.append("usemtl " + "abc"[block % 3])
+        for _ in range(int(rng.integers(3, 40))):
+            x, y, z = rng.normal(size=3)
+            lines.append(f"v {x:.6f} {y:.6f} {z:.6f}" + ("\r" if block % 7 == 0 else ""))
+            nv += 1
+            if rng.random() < 0.2:
+                lines.append(f"vn {rng.normal():.4f} {rng.normal():.4f} {rng.normal():.4f}")
+        for _ in range(int(rng.integers(1, 30))):
+            ids = rng.choice(nv, 3, replace=False)
+            style = rng.integers(0, 3)
+            if style == 0:
+                lines.append("f " + " ".join(str(i + 1) for i in ids))
+            elif style == 1:
+                lines.append("f " + " ".join(str(int(i) - nv) for i in ids))         # relative ids
+            else:
+                lines.append("f " + " ".join(f"{i + 1}/1/{i + 1}" for i in ids))
+        if block % 5 == 0:
+            lines.append("")
+    p = tmp_path / "sliced.obj"
+    p.write_text("\n".join(lines) + "\n")
+    monkeypatch.setenv("RT_LOAD_THREADS", "1")
+    ref = capi.Mesh(str(p)).arrays()
+    assert ref[0].shape[0] > 500
+    for n in (2, 3, 7, 16, 64):
+        monkeypatch.setenv("RT_LOAD_THREADS", str(n))
+        got = capi.Mesh(str(p)).arrays()
+        assert all(a.shape == b.shape for a, b in zip(got, ref)), n
+        assert _bits(got[0], ref[0]) == 0 and _bits(got[1], ref[1]) == 0 and _bits(got[2], ref[2]) == 0, n
+        assert (got[3] == ref[3]).all() and (got[4] == ref[4]).all(), n
+    # a relative id that reaches before the first vertex of the file is an error in every slicing
+    q = tmp_path / "bad_rel.obj"
+    q.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\n" + "f 1 2 3\n" * 40 + "f 1 2 -4\n" + "v 2 2 2\n" * 40)
+    for n in (1, 5):
+        monkeypatch.setenv("RT_LOAD_THREADS", str(n))
+        with pytest.raises(capi.RtError) as e:
+            capi.Mesh(str(q))
+        assert e.value.code == -4
